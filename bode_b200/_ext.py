@@ -1,0 +1,143 @@
+"""ctypes binding of ``libbode_b200.so`` (the C ABI declared in ``include/bode_b200.h``).
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is usable every compute call raises.
+PyTorch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libbode_b200.so")
+
+BODE_FORM_REFERENCE = 0
+BODE_FORM_LOG1P = 1
+BODE_MAX_N = 1024
+BODE_MAX_D = 16
+
+EXPORTS = (
+    "bode_version", "bode_strerror", "bode_last_cuda_error", "bode_ekld_workspace_bytes", "bode_ekld_prepare_dev",
+    "bode_ekld_sample_terms_dev", "bode_ekld_mu_sigma_dev", "bode_ekld_score_scratch_bytes", "bode_ekld_score_dev",
+    "bode_us_variance_dev", "bode_ekld_score_host", "bode_gp_loglik_host", "bode_fp64_peak",
+)
+
+
+class BodeError(RuntimeError):
+    """A non-zero status returned across the C ABI."""
+
+    def __init__(self, status, detail=""):
+        self.status = status
+        super().__init__("bode_b200 status %d: %s" % (status, detail))
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (built in-tree by ``__graft_entry__.build()`` / ``make -C bode_b200/csrc``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "bode_b200: %s not found -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    c_dp = ctypes.c_void_p
+    lib.bode_version.restype = ctypes.c_char_p
+    lib.bode_strerror.restype = ctypes.c_char_p
+    lib.bode_strerror.argtypes = [ctypes.c_int]
+    lib.bode_last_cuda_error.restype = ctypes.c_char_p
+    lib.bode_ekld_workspace_bytes.restype = ctypes.c_size_t
+    lib.bode_ekld_workspace_bytes.argtypes = [ctypes.c_int] * 3
+    lib.bode_ekld_prepare_dev.restype = ctypes.c_int
+    lib.bode_ekld_prepare_dev.argtypes = [c_dp, c_dp, c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_double, ctypes.c_double, c_dp, ctypes.c_size_t, c_dp, c_dp]
+    lib.bode_ekld_sample_terms_dev.restype = ctypes.c_int
+    lib.bode_ekld_sample_terms_dev.argtypes = [c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_dp, c_dp]
+    lib.bode_ekld_mu_sigma_dev.restype = ctypes.c_int
+    lib.bode_ekld_mu_sigma_dev.argtypes = [c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_dp, c_dp]
+    lib.bode_ekld_score_scratch_bytes.restype = ctypes.c_size_t
+    lib.bode_ekld_score_scratch_bytes.argtypes = [ctypes.c_int64]
+    lib.bode_ekld_score_dev.restype = ctypes.c_int
+    lib.bode_ekld_score_dev.argtypes = [c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_dp, ctypes.c_int64,
+                                        ctypes.c_int64, ctypes.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]
+    lib.bode_us_variance_dev.restype = ctypes.c_int
+    lib.bode_us_variance_dev.argtypes = [c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_dp, ctypes.c_int64,
+                                         ctypes.c_int64, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]
+    lib.bode_ekld_score_host.restype = ctypes.c_int
+    lib.bode_ekld_score_host.argtypes = [c_dp, c_dp, c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_double, ctypes.c_double, c_dp, ctypes.c_int64, ctypes.c_int,
+                                         c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]
+    lib.bode_gp_loglik_host.restype = ctypes.c_int
+    lib.bode_gp_loglik_host.argtypes = [c_dp, c_dp, c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_double, ctypes.c_double, c_dp]
+    lib.bode_fp64_peak.restype = ctypes.c_int
+    lib.bode_fp64_peak.argtypes = [c_dp, c_dp]
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != 0:
+        lib = load()
+        detail = lib.bode_strerror(status).decode()
+        if status == -4:
+            detail += " (" + lib.bode_last_cuda_error().decode() + ")"
+        raise BodeError(status, detail)
+
+
+def _np_ptr(a):
+    return ctypes.c_void_p(a.ctypes.data) if a is not None else None
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def ekld_score_host(X, Y, hyp, X_design, nugget_var, jitter=1e-8, form=BODE_FORM_REFERENCE, want_var=True,
+                    want_kld=False, raise_not_pd=True):
+    """Host-buffer call (``bode_ekld_score_host``): NumPy in, NumPy out; copies both ways inside the call."""
+    lib = load()
+    X = _f64(X); n, d = X.shape
+    Y = _f64(Y).reshape(-1)
+    hyp = _f64(hyp); S, ndim = hyp.shape
+    Xd = _f64(np.atleast_2d(X_design)); Nd = Xd.shape[0]
+    assert Xd.shape[1] == d and Y.shape[0] == n
+    score = np.empty(Nd)
+    var = np.empty(Nd) if want_var else None
+    kld = np.empty((S, Nd)) if want_kld else None
+    best = np.zeros(1, dtype=np.int64)
+    ms = np.empty(2)
+    info = np.zeros(S, dtype=np.int32)
+    st = lib.bode_ekld_score_host(_np_ptr(X), _np_ptr(Y), _np_ptr(hyp), n, d, S, ndim, float(nugget_var), float(jitter),
+                                  _np_ptr(Xd), Nd, int(form), _np_ptr(score), _np_ptr(var), _np_ptr(kld), _np_ptr(best),
+                                  _np_ptr(ms), _np_ptr(info))
+    if st != 0 and not (st == -5 and not raise_not_pd):
+        check(st)
+    return dict(score=score, var=var, kld=kld, argmax=int(best[0]), mu_Q=float(ms[0]), sigma_Q=float(ms[1]), info=info)
+
+
+def gp_loglik_host(X, Y, hyp, nugget_var, jitter=1e-8):
+    lib = load()
+    X = _f64(X); n, d = X.shape
+    Y = _f64(Y).reshape(-1)
+    hyp = _f64(np.atleast_2d(hyp)); S, ndim = hyp.shape
+    out = np.empty(S)
+    check(lib.bode_gp_loglik_host(_np_ptr(X), _np_ptr(Y), _np_ptr(hyp), n, d, S, ndim, float(nugget_var), float(jitter),
+                                  _np_ptr(out)))
+    return out
+
+
+def fp64_peak():
+    lib = load()
+    a = ctypes.c_double(0.0)
+    b = ctypes.c_double(0.0)
+    check(lib.bode_fp64_peak(ctypes.byref(a), ctypes.byref(b)))
+    return dict(dmma_tflops=a.value, dfma_tflops=b.value)

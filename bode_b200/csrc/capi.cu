@@ -1,0 +1,264 @@
+// C ABI of bode_b200 (see include/bode_b200.h).  Thin, allocation-free glue around the kernels for the *_dev
+// entry points; the *_host entry points own their device scratch for the duration of the call.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <vector>
+
+#include "../../include/bode_b200.h"
+#include "layout.h"
+#include "prepare_args.h"
+#include "score_args.h"
+
+namespace bode {
+cudaError_t launch_prepare(const PrepArgs& a, cudaStream_t st);
+cudaError_t launch_sample_terms(const void* ws, const Layout& L, double* out, cudaStream_t st);
+cudaError_t launch_mu_sigma(const void* ws, const Layout& L, double* out, cudaStream_t st);
+int plan_score(const Layout& L, int64_t Nd, int sm_count, size_t smem_optin, ScorePlan* P);
+cudaError_t launch_score(const ScoreArgs& a, const ScorePlan& P, cudaStream_t st);
+cudaError_t launch_reduce(const double* logk, int S, int64_t Nd, int64_t idx_offset, double* score, double* var,
+                          double* part_val, int64_t* part_idx, double* best, int64_t* best_idx, cudaStream_t st);
+cudaError_t launch_exp_inplace(double* v, size_t n, cudaStream_t st);
+cudaError_t measure_fp64_peak(double* dmma, double* dfma);
+}  // namespace bode
+
+using namespace bode;
+
+static thread_local char g_cuda_err[256] = "";
+
+static int cuda_fail(cudaError_t e, const char* where) {
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", where, cudaGetErrorString(e));
+  return BODE_ERR_CUDA;
+}
+#define BODE_CUDA(call)                                  \
+  do {                                                   \
+    cudaError_t e__ = (call);                            \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+struct DevProps {
+  int sm_count;
+  size_t smem_optin;
+};
+static int get_props(DevProps* p) {
+  static std::mutex mu;
+  static std::vector<DevProps> cache;
+  int dev = 0;
+  BODE_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  if ((int)cache.size() <= dev) cache.resize(dev + 1, DevProps{0, 0});
+  if (cache[dev].sm_count == 0) {
+    int sm = 0, optin = 0;
+    BODE_CUDA(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev));
+    BODE_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    cache[dev].sm_count = sm;
+    cache[dev].smem_optin = (size_t)optin;
+  }
+  *p = cache[dev];
+  return BODE_OK;
+}
+
+static bool shape_ok(int n, int d, int S) { return n >= 1 && d >= 1 && S >= 1; }
+static bool shape_supported(int n, int d) { return n <= BODE_MAX_N && d <= BODE_MAX_D; }
+
+// ---- host-buffer entry points --------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+  template <typename T> T* as() { return static_cast<T*>(p); }
+};
+
+extern "C" {
+
+const char* bode_version(void) { return "bode_b200 0.1.0 (sm_100a)"; }
+
+const char* bode_strerror(int status) {
+  switch (status) {
+    case BODE_OK: return "ok";
+    case BODE_ERR_BAD_ARG: return "bad argument";
+    case BODE_ERR_UNSUPPORTED: return "unsupported shape (n > 1024 or d > 16)";
+    case BODE_ERR_WORKSPACE: return "workspace too small or misaligned";
+    case BODE_ERR_CUDA: return "CUDA error";
+    case BODE_ERR_NOT_PD: return "covariance matrix not positive definite";
+    default: return "unknown status";
+  }
+}
+
+const char* bode_last_cuda_error(void) { return g_cuda_err; }
+
+size_t bode_ekld_workspace_bytes(int n, int d, int S) {
+  if (!shape_ok(n, d, S) || !shape_supported(n, d)) return 0;
+  return make_layout(n, d, S).total_bytes;
+}
+
+int bode_ekld_prepare_dev(const double* X, const double* Y, const double* hyp, int n, int d, int S, int ndim,
+                          double nugget_var, double jitter, void* workspace, size_t workspace_bytes, int* info,
+                          void* stream) {
+  if (!X || !Y || !hyp || !workspace || !info || !shape_ok(n, d, S)) return BODE_ERR_BAD_ARG;
+  if (ndim != d + 1 && ndim != d + 2) return BODE_ERR_BAD_ARG;
+  if (!shape_supported(n, d)) return BODE_ERR_UNSUPPORTED;
+  PrepArgs a;
+  a.X = X; a.Y = Y; a.hyp = hyp; a.n = n; a.d = d; a.S = S; a.ndim = ndim;
+  a.nugget_var = nugget_var; a.jitter = jitter;
+  a.ws = static_cast<char*>(workspace);
+  a.L = make_layout(n, d, S);
+  a.info = info;
+  if (workspace_bytes < a.L.total_bytes || (reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return BODE_ERR_WORKSPACE;
+  BODE_CUDA(launch_prepare(a, static_cast<cudaStream_t>(stream)));
+  return BODE_OK;
+}
+
+int bode_ekld_sample_terms_dev(const void* workspace, int n, int d, int S, double* out, void* stream) {
+  if (!workspace || !out || !shape_ok(n, d, S)) return BODE_ERR_BAD_ARG;
+  if (!shape_supported(n, d)) return BODE_ERR_UNSUPPORTED;
+  BODE_CUDA(launch_sample_terms(workspace, make_layout(n, d, S), out, static_cast<cudaStream_t>(stream)));
+  return BODE_OK;
+}
+
+int bode_ekld_mu_sigma_dev(const void* workspace, int n, int d, int S, double* out, void* stream) {
+  if (!workspace || !out || !shape_ok(n, d, S)) return BODE_ERR_BAD_ARG;
+  if (!shape_supported(n, d)) return BODE_ERR_UNSUPPORTED;
+  BODE_CUDA(launch_mu_sigma(workspace, make_layout(n, d, S), out, static_cast<cudaStream_t>(stream)));
+  return BODE_OK;
+}
+
+size_t bode_ekld_score_scratch_bytes(int64_t Nd) {
+  if (Nd < 1) return 0;
+  const size_t nb = (size_t)((Nd + 255) / 256);
+  return align_up(nb * sizeof(double), 256) + align_up(nb * sizeof(int64_t), 256);
+}
+
+static int score_common(const void* workspace, int n, int d, int S, const double* Xd, int64_t Nd, int64_t idx_offset,
+                        int form, int mode, double* logk, double* score, double* var, double* best, int64_t* best_idx,
+                        void* scratch, void* stream) {
+  if (!workspace || !Xd || !logk || !score || !best || !best_idx || !scratch || !shape_ok(n, d, S) || Nd < 1)
+    return BODE_ERR_BAD_ARG;
+  if (form != BODE_FORM_REFERENCE && form != BODE_FORM_LOG1P) return BODE_ERR_BAD_ARG;
+  if (!shape_supported(n, d)) return BODE_ERR_UNSUPPORTED;
+  DevProps props;
+  int rc = get_props(&props);
+  if (rc != BODE_OK) return rc;
+  ScorePlan P;
+  const Layout L = make_layout(n, d, S);
+  if (plan_score(L, Nd, props.sm_count, props.smem_optin, &P) != 0) return BODE_ERR_UNSUPPORTED;
+  ScoreArgs a;
+  a.ws = workspace; a.L = L; a.Xd = Xd; a.Nd = Nd; a.logk = logk; a.S = S;
+  a.sc = P.sc; a.ntiles = P.ntiles; a.form = form; a.mode = mode;
+  a.stages = P.stages; a.chunk_max = P.chunk_max; a.nchunks = P.nchunks;
+  memcpy(a.chunk_g0, P.chunk_g0, sizeof(a.chunk_g0));
+  memcpy(a.tile_id, P.tile_id, sizeof(a.tile_id));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BODE_CUDA(launch_score(a, P, st));
+  const size_t nb = (size_t)((Nd + 255) / 256);
+  double* part_val = static_cast<double*>(scratch);
+  int64_t* part_idx = reinterpret_cast<int64_t*>(static_cast<char*>(scratch) + align_up(nb * sizeof(double), 256));
+  BODE_CUDA(launch_reduce(logk, S, Nd, idx_offset, score, var, part_val, part_idx, best, best_idx, st));
+  return BODE_OK;
+}
+
+int bode_ekld_score_dev(const void* workspace, int n, int d, int S, const double* X_design, int64_t Nd,
+                        int64_t idx_offset, int form, double* logk, double* score, double* var, double* best,
+                        int64_t* best_idx, void* scratch, void* stream) {
+  return score_common(workspace, n, d, S, X_design, Nd, idx_offset, form, kModeEkld, logk, score, var, best, best_idx,
+                      scratch, stream);
+}
+
+int bode_us_variance_dev(const void* workspace, int n, int d, int S, const double* X_grid, int64_t Ng,
+                         int64_t idx_offset, double* sigx, double* pred_var, double* best, int64_t* best_idx,
+                         void* scratch, void* stream) {
+  return score_common(workspace, n, d, S, X_grid, Ng, idx_offset, BODE_FORM_REFERENCE, kModeVariance, sigx, pred_var,
+                      nullptr, best, best_idx, scratch, stream);
+}
+
+int bode_ekld_score_host(const double* X, const double* Y, const double* hyp, int n, int d, int S, int ndim,
+                         double nugget_var, double jitter, const double* X_design, int64_t Nd, int form,
+                         double* score, double* var, double* kld, int64_t* best_idx, double* mu_sigma, int* info) {
+  if (!X || !Y || !hyp || !X_design || !score || !shape_ok(n, d, S) || Nd < 1) return BODE_ERR_BAD_ARG;
+  if (ndim != d + 1 && ndim != d + 2) return BODE_ERR_BAD_ARG;
+  if (!shape_supported(n, d)) return BODE_ERR_UNSUPPORTED;
+  const size_t wsb = bode_ekld_workspace_bytes(n, d, S);
+  DevBuf dX, dY, dH, dXd, dWs, dInfo, dLogk, dScore, dVar, dBest, dBestIdx, dScr, dMs;
+  BODE_CUDA(dX.alloc(sizeof(double) * n * d));
+  BODE_CUDA(dY.alloc(sizeof(double) * n));
+  BODE_CUDA(dH.alloc(sizeof(double) * S * ndim));
+  BODE_CUDA(dXd.alloc(sizeof(double) * Nd * d));
+  BODE_CUDA(dWs.alloc(wsb));
+  BODE_CUDA(dInfo.alloc(sizeof(int) * S));
+  BODE_CUDA(dLogk.alloc(sizeof(double) * (size_t)S * Nd));
+  BODE_CUDA(dScore.alloc(sizeof(double) * Nd));
+  BODE_CUDA(dVar.alloc(sizeof(double) * Nd));
+  BODE_CUDA(dBest.alloc(sizeof(double)));
+  BODE_CUDA(dBestIdx.alloc(sizeof(int64_t)));
+  BODE_CUDA(dScr.alloc(bode_ekld_score_scratch_bytes(Nd)));
+  BODE_CUDA(dMs.alloc(2 * sizeof(double)));
+  BODE_CUDA(cudaMemcpy(dX.p, X, sizeof(double) * n * d, cudaMemcpyHostToDevice));
+  BODE_CUDA(cudaMemcpy(dY.p, Y, sizeof(double) * n, cudaMemcpyHostToDevice));
+  BODE_CUDA(cudaMemcpy(dH.p, hyp, sizeof(double) * S * ndim, cudaMemcpyHostToDevice));
+  BODE_CUDA(cudaMemcpy(dXd.p, X_design, sizeof(double) * Nd * d, cudaMemcpyHostToDevice));
+  int rc = bode_ekld_prepare_dev(dX.as<double>(), dY.as<double>(), dH.as<double>(), n, d, S, ndim, nugget_var, jitter,
+                                 dWs.p, wsb, dInfo.as<int>(), nullptr);
+  if (rc != BODE_OK) return rc;
+  rc = bode_ekld_score_dev(dWs.p, n, d, S, dXd.as<double>(), Nd, 0, form, dLogk.as<double>(), dScore.as<double>(),
+                           var ? dVar.as<double>() : nullptr, dBest.as<double>(), dBestIdx.as<int64_t>(), dScr.p, nullptr);
+  if (rc != BODE_OK) return rc;
+  if (mu_sigma) {
+    rc = bode_ekld_mu_sigma_dev(dWs.p, n, d, S, dMs.as<double>(), nullptr);
+    if (rc != BODE_OK) return rc;
+    BODE_CUDA(cudaMemcpy(mu_sigma, dMs.p, 2 * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  BODE_CUDA(cudaMemcpy(score, dScore.p, sizeof(double) * Nd, cudaMemcpyDeviceToHost));
+  if (var) BODE_CUDA(cudaMemcpy(var, dVar.p, sizeof(double) * Nd, cudaMemcpyDeviceToHost));
+  if (best_idx) BODE_CUDA(cudaMemcpy(best_idx, dBestIdx.p, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  if (kld) {
+    BODE_CUDA(launch_exp_inplace(dLogk.as<double>(), (size_t)S * Nd, nullptr));
+    BODE_CUDA(cudaMemcpy(kld, dLogk.p, sizeof(double) * (size_t)S * Nd, cudaMemcpyDeviceToHost));
+  }
+  std::vector<int> hinfo(S);
+  BODE_CUDA(cudaMemcpy(hinfo.data(), dInfo.p, sizeof(int) * S, cudaMemcpyDeviceToHost));
+  BODE_CUDA(cudaDeviceSynchronize());
+  int bad = 0;
+  for (int s = 0; s < S; s++) {
+    if (info) info[s] = hinfo[s];
+    if (hinfo[s] != 0) bad = 1;
+  }
+  return bad ? BODE_ERR_NOT_PD : BODE_OK;
+}
+
+int bode_gp_loglik_host(const double* X, const double* Y, const double* hyp, int n, int d, int S, int ndim,
+                        double nugget_var, double jitter, double* loglik) {
+  if (!X || !Y || !hyp || !loglik || !shape_ok(n, d, S)) return BODE_ERR_BAD_ARG;
+  if (ndim != d + 1 && ndim != d + 2) return BODE_ERR_BAD_ARG;
+  if (!shape_supported(n, d)) return BODE_ERR_UNSUPPORTED;
+  const size_t wsb = bode_ekld_workspace_bytes(n, d, S);
+  DevBuf dX, dY, dH, dWs, dInfo, dT;
+  BODE_CUDA(dX.alloc(sizeof(double) * n * d));
+  BODE_CUDA(dY.alloc(sizeof(double) * n));
+  BODE_CUDA(dH.alloc(sizeof(double) * S * ndim));
+  BODE_CUDA(dWs.alloc(wsb));
+  BODE_CUDA(dInfo.alloc(sizeof(int) * S));
+  BODE_CUDA(dT.alloc(sizeof(double) * S * kConsts));
+  BODE_CUDA(cudaMemcpy(dX.p, X, sizeof(double) * n * d, cudaMemcpyHostToDevice));
+  BODE_CUDA(cudaMemcpy(dY.p, Y, sizeof(double) * n, cudaMemcpyHostToDevice));
+  BODE_CUDA(cudaMemcpy(dH.p, hyp, sizeof(double) * S * ndim, cudaMemcpyHostToDevice));
+  int rc = bode_ekld_prepare_dev(dX.as<double>(), dY.as<double>(), dH.as<double>(), n, d, S, ndim, nugget_var, jitter,
+                                 dWs.p, wsb, dInfo.as<int>(), nullptr);
+  if (rc != BODE_OK) return rc;
+  rc = bode_ekld_sample_terms_dev(dWs.p, n, d, S, dT.as<double>(), nullptr);
+  if (rc != BODE_OK) return rc;
+  std::vector<double> t((size_t)S * kConsts);
+  BODE_CUDA(cudaMemcpy(t.data(), dT.p, sizeof(double) * S * kConsts, cudaMemcpyDeviceToHost));
+  for (int s = 0; s < S; s++) loglik[s] = t[(size_t)s * kConsts + C_LOGLIK];
+  return BODE_OK;
+}
+
+int bode_fp64_peak(double* dmma_tflops, double* dfma_tflops) {
+  if (!dmma_tflops || !dfma_tflops) return BODE_ERR_BAD_ARG;
+  BODE_CUDA(measure_fp64_peak(dmma_tflops, dfma_tflops));
+  return BODE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+// Device-workspace layout shared by the prepare (K1) and scoring (K2-K4) kernels and the host C ABI.
+//
+// Per hyper-sample s the workspace holds
+//   aux[s]   : one contiguous block (copied to shared memory with a single bulk copy by the scoring kernel)
+//                consts[8]  = {variance, noise_var, sigma0, sigma1, mu1, logdet, Y^T A^-1 Y, loglik}
+//                ck[16]     = 1/(sqrt(2) ell_k)            (zero padded)
+//                ell[16]    = ell_k                        (one padded)
+//                w[npad]    = A^-1 e                       (zero padded)
+//                U[npad][dpad] = X[j][k] * ck[k]           (zero padded rows / columns)
+//   M[s]     : L_s^-1 in the "k4-group major, live row-tile suffix" tiling the DMMA mainloop consumes:
+//                for g = 0..ng-1 (columns j = 4g..4g+3), for R = g/2..nrt-1 (rows 8R..8R+7): a 256-byte block
+//                holding M[8R+rr][4g+kk] at [rr*4 + kk] -- exactly the A-fragment order of mma.m8n8k4.f64.
+//                Row tiles R < g/2 lie strictly above the diagonal and are not stored.
+//   Lw[s]    : (n+2) x npad row-major scratch: Cholesky factor rows 0..n-1, then a = L^-1 e and z = L^-1 Y.
+//   Xw[s]    : n x npad row-major scratch: M^T (row r = column r of L^-1).
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define BODE_HD __host__ __device__ __forceinline__
+#else
+#define BODE_HD inline
+#endif
+
+namespace bode {
+
+constexpr int kConsts = 8;
+constexpr int kCkPad = 16;
+enum ConstIdx { C_SS = 0, C_NOISE = 1, C_SIGMA0 = 2, C_SIGMA1 = 3, C_MU1 = 4, C_LOGDET = 5, C_QUAD = 6, C_LOGLIK = 7 };
+
+struct Layout {
+  int n, d, S;
+  int nrt;   // row tiles of 8
+  int npad;  // 8 * nrt
+  int ng;    // k4 groups = 2 * nrt
+  int dpad;  // d rounded up to even (16-byte rows of U)
+  size_t aux_doubles;  // per sample
+  size_t m_doubles;    // per sample
+  size_t lw_doubles;   // per sample
+  size_t xw_doubles;   // per sample
+  size_t off_aux, off_m, off_lw, off_xw, total_bytes;  // byte offsets of the four sections
+};
+
+BODE_HD size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+BODE_HD Layout make_layout(int n, int d, int S) {
+  Layout L;
+  L.n = n; L.d = d; L.S = S;
+  L.nrt = (n + 7) / 8;
+  L.npad = 8 * L.nrt;
+  L.ng = 2 * L.nrt;
+  L.dpad = (d + 1) & ~1;
+  L.aux_doubles = (size_t)kConsts + 2 * kCkPad + L.npad + (size_t)L.npad * L.dpad;
+  L.m_doubles = (size_t)32 * L.nrt * (L.nrt + 1);
+  L.lw_doubles = (size_t)(n + 2) * L.npad;
+  L.xw_doubles = (size_t)n * L.npad;
+  L.off_aux = 0;
+  L.off_m = align_up(L.off_aux + sizeof(double) * L.aux_doubles * S, 256);
+  L.off_lw = align_up(L.off_m + sizeof(double) * L.m_doubles * S, 256);
+  L.off_xw = align_up(L.off_lw + sizeof(double) * L.lw_doubles * S, 256);
+  L.total_bytes = align_up(L.off_xw + sizeof(double) * L.xw_doubles * S, 256);
+  return L;
+}
+
+// aux sub-offsets (doubles)
+BODE_HD int aux_ck() { return kConsts; }
+BODE_HD int aux_ell() { return kConsts + kCkPad; }
+BODE_HD int aux_w() { return kConsts + 2 * kCkPad; }
+BODE_HD int aux_u(const Layout& L) { return kConsts + 2 * kCkPad + L.npad; }
+
+// offset (doubles) of k4-group g inside a sample's tiled M; block (R, g), R >= g/2, sits at m_goff(g) + (R - g/2)*32
+BODE_HD size_t m_goff(int nrt, int g) {
+  const size_t a = (size_t)(g >> 1), b = (size_t)(g & 1);
+  return 32 * (2 * (a * nrt - a * (a - 1) / 2) + b * (nrt - a));
+}
+
+}  // namespace bode

@@ -1,0 +1,525 @@
+// K2+K3+K4 -- dense EKLD scoring of a candidate block under every hyper-sample (sm_100a).
+//
+// Replaces N_d * S evaluations of avg_kld_mean (reference bode/_sampler.py:464-481) and of the helpers it calls
+// (get_params_2 :391-402, predict / kern.K inside GPy, xik _core.py:86-92), and the log / mean / var / argmax of
+// mcmc_kld + optimize (:492, :659).  Per (candidate x, hyper-sample s):
+//     k   = K_ARD-RBF(X, x; theta_s)            (K2, phase A: direct-difference distance + exp, never leaves smem)
+//     xi  = xik(x)                               (K2, closed form, 2d erf)
+//     t   = L_s^-1 k ; sigma_x = ss - t.t        (K3, phase B: FP64 tensor-core DMMA.8x8x4 against the tiled L^-1)
+//     v   = xi - w_s.k                           (K3, folded into phase A)
+//     EKLD = log(sqrt(s1)/sqrt(s2)) + s2/(2 s1) + (v^2/s1/(sigma_x+noise))*0.5 - 0.5 ; logk = log(EKLD)   (K4)
+//
+// Work decomposition: one CTA = one work item = (tile of C candidates) x (chunk of SC hyper-samples).  Per
+// sample the CTA runs phase A (8 compute warps fill Kc[npad][C] in shared memory), phase B (each warp owns up to
+// RT row tiles x CT column tiles of T = L^-1 Kc as DMMA accumulators; L^-1 streams through a shared-memory ring
+// filled by a dedicated producer warp with 1-D bulk copies (TMA, cp.async.bulk + mbarrier)), and a small epilogue.
+// log EKLD goes to logk[S][Nd]; a second kernel reduces over s sequentially (deterministic, independent of how
+// candidates were tiled or sharded across GPUs) and does the block argmax; a third picks the global winner.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "layout.h"
+#include "score_args.h"
+
+namespace bode {
+
+// ----------------------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier, 1-D bulk copy (TMA), DMMA
+// ----------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void compute_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kComputeThreads) : "memory"); }
+
+// ----------------------------------------------------------------------------------------------------------------
+// Phase A: Kc[(g*C + c)*4 + kk] = ss * exp(-sum_k (U[4g+kk][k] - x_c[k] ck[k])^2); partial w.k; partial xik factors
+// ----------------------------------------------------------------------------------------------------------------
+template <int DP, int C>
+__device__ __forceinline__ void phase_a(const double* __restrict__ aux, int aux_u_off, int dpad, int ng, int d,
+                                        const double* __restrict__ xt, double* __restrict__ Kc,
+                                        double* __restrict__ pv, double* __restrict__ xip, int tid) {
+  constexpr int NJQ = kComputeThreads / C;
+  const int c = tid % C, jq = tid / C;
+  const double ss = aux[C_SS];
+  const double* ck = aux + aux_ck();
+  const double* ell = aux + aux_ell();
+  const double* w = aux + aux_w();
+  const double* U = aux + aux_u_off;
+  double y[DP];
+#pragma unroll
+  for (int k = 0; k < DP; k++) y[k] = (k < d) ? xt[c * kXtStride + k] * ck[k] : 0.0;
+  double wk = 0.0;
+  for (int g = jq; g < ng; g += NJQ) {
+    double r2[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+      const double* uj = U + (size_t)(4 * g + kk) * dpad;
+      if (DP == 1) {
+        const double t = uj[0] - y[0];
+        r2[kk] = t * t;
+      } else {
+#pragma unroll
+        for (int k2 = 0; k2 < DP / 2; k2++) {
+          const double2 u = *reinterpret_cast<const double2*>(uj + 2 * k2);
+          const double t0 = u.x - y[2 * k2], t1 = u.y - y[2 * k2 + 1];
+          r2[kk] = fma(t0, t0, r2[kk]);
+          r2[kk] = fma(t1, t1, r2[kk]);
+        }
+        if (DP & 1) {
+          const double t = uj[DP - 1] - y[DP - 1];
+          r2[kk] = fma(t, t, r2[kk]);
+        }
+      }
+    }
+    double kv[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) kv[kk] = ss * exp(-r2[kk]);
+    const double2 w01 = *reinterpret_cast<const double2*>(w + 4 * g);
+    const double2 w23 = *reinterpret_cast<const double2*>(w + 4 * g + 2);
+    wk = fma(w01.x, kv[0], wk);
+    wk = fma(w01.y, kv[1], wk);
+    wk = fma(w23.x, kv[2], wk);
+    wk = fma(w23.y, kv[3], wk);
+    double2* dst = reinterpret_cast<double2*>(Kc + ((size_t)g * C + c) * 4);
+    dst[0] = make_double2(kv[0], kv[1]);
+    dst[1] = make_double2(kv[2], kv[3]);
+  }
+  pv[jq * C + c] = wk;
+  // xik factors of the dimensions k == jq (mod NJQ): sqrt(pi)/sqrt(2) * ell_k * (erf((1-x) ck) - erf((0-x) ck))
+  double xf = 1.0;
+  for (int k = jq; k < d; k += NJQ) {
+    const double x = xt[c * kXtStride + k];
+    xf *= 1.2533141373155001 * ell[k] * (erf((1.0 - x) * ck[k]) - erf((0.0 - x) * ck[k]));
+  }
+  xip[jq * C + c] = xf;
+}
+
+template <int C>
+__device__ __forceinline__ void phase_a_dispatch(const double* aux, int aux_u_off, int dpad, int ng, int d,
+                                                 const double* xt, double* Kc, double* pv, double* xip, int tid) {
+  switch (d) {
+#define BODE_CASE(D)                                                          \
+  case D:                                                                     \
+    phase_a<D, C>(aux, aux_u_off, dpad, ng, d, xt, Kc, pv, xip, tid);         \
+    break;
+    BODE_CASE(1) BODE_CASE(2) BODE_CASE(3) BODE_CASE(4) BODE_CASE(5) BODE_CASE(6) BODE_CASE(7) BODE_CASE(8)
+    BODE_CASE(9) BODE_CASE(10) BODE_CASE(11) BODE_CASE(12) BODE_CASE(13) BODE_CASE(14) BODE_CASE(15) BODE_CASE(16)
+#undef BODE_CASE
+    default:
+      break;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// The scoring kernel.  RT = row tiles per warp row-group (4 row groups), CT = column tiles per warp (2 col groups).
+// ----------------------------------------------------------------------------------------------------------------
+template <int RT, int CT>
+__global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constant__ ScoreArgs a) {
+  constexpr int C = 16 * CT;  // candidates per CTA
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const Layout& L = a.L;
+  const int nrt = L.nrt, ng = L.ng, npad = L.npad;
+
+  // ---- shared memory carve-up (offsets in doubles; everything 16-byte aligned) ----
+  double* Kc = reinterpret_cast<double*>(smem_raw);             // [ng][C][4]
+  double* auxs = Kc + (size_t)npad * C;                          // aux block of the current sample
+  double* ring = auxs + L.aux_doubles;                           // [stages][chunk_max]
+  double* red = ring + (size_t)a.stages * a.chunk_max;           // [4][C]
+  double* pv = red + 4 * C;                                      // [2][NJQ][C]   (NJQ*C = 256)
+  double* xip = pv + 2 * kComputeThreads;                        // [2][NJQ][C]
+  double* xt = xip + 2 * kComputeThreads;                        // [C][kXtStride]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xt + C * kXtStride);
+  uint64_t* full = bars;                  // [stages]
+  uint64_t* empty = bars + kMaxStages;    // [stages]
+  uint64_t* aux_full = bars + 2 * kMaxStages;
+  uint64_t* aux_empty = aux_full + 1;
+
+  // ---- work item ----
+  const int item = blockIdx.x;
+  const int sch = item / a.ntiles, tile = item - sch * a.ntiles;
+  const int s_begin = sch * a.sc, s_end = min(a.S, s_begin + a.sc);
+  const int64_t c0 = (int64_t)tile * C;
+
+  if (tid == 0) {
+    for (int i = 0; i < a.stages; i++) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], kComputeWarps);
+    }
+    mbar_init(aux_full, 1);
+    mbar_init(aux_empty, kComputeWarps);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // candidate tile -> smem (rows beyond Nd are filled with a harmless interior point)
+  for (int idx = tid; idx < C * kXtStride; idx += kScoreThreads) {
+    const int c = idx / kXtStride, k = idx - c * kXtStride;
+    double v = 0.5;
+    if (k < L.d && c0 + c < a.Nd) v = a.Xd[(c0 + c) * L.d + k];
+    xt[idx] = v;
+  }
+  __syncthreads();
+
+  const char* wsb = static_cast<const char*>(a.ws);
+  const double* aux_g = reinterpret_cast<const double*>(wsb + L.off_aux);
+  const double* m_g = reinterpret_cast<const double*>(wsb + L.off_m);
+  const uint32_t aux_bytes = (uint32_t)(L.aux_doubles * sizeof(double));
+
+  if (warp == kComputeWarps) {
+    // ===================================== producer warp (one elected lane) =====================================
+    if (lane == 0) {
+      uint32_t it = 0;  // running chunk counter -> ring stage / parity
+      for (int s = s_begin; s < s_end; s++) {
+        const int ls = s - s_begin;
+        if (ls > 0) mbar_wait(aux_empty, (uint32_t)((ls - 1) & 1));
+        mbar_arrive_expect_tx(aux_full, aux_bytes);
+        bulk_copy_g2s(auxs, aux_g + (size_t)s * L.aux_doubles, aux_bytes, aux_full);
+        const double* ms = m_g + (size_t)s * L.m_doubles;
+        for (int q = 0; q < a.nchunks; q++, it++) {
+          const uint32_t st = it % (uint32_t)a.stages, round = it / (uint32_t)a.stages;
+          if (round > 0) mbar_wait(&empty[st], (round - 1) & 1);
+          const size_t o0 = m_goff(nrt, a.chunk_g0[q]), o1 = m_goff(nrt, a.chunk_g0[q + 1]);
+          const uint32_t bytes = (uint32_t)((o1 - o0) * sizeof(double));
+          mbar_arrive_expect_tx(&full[st], bytes);
+          bulk_copy_g2s(ring + (size_t)st * a.chunk_max, ms + o0, bytes, &full[st]);
+        }
+      }
+    }
+    return;
+  }
+
+  // ========================================== compute warps ======================================================
+  const int rg = warp & 3, cg = warp >> 2;
+  const int cbase = cg * CT * 8;
+  int tiles[RT];
+#pragma unroll
+  for (int t = 0; t < RT; t++) tiles[t] = a.tile_id[rg * kMaxRT + t];
+
+  const int aux_u_off = aux_u(L);
+  uint32_t it = 0;
+  for (int s = s_begin; s < s_end; s++) {
+    const int ls = s - s_begin, par = ls & 1;
+    double* pvp = pv + par * kComputeThreads;
+    double* xipp = xip + par * kComputeThreads;
+    // ---- phase A ----
+    mbar_wait(aux_full, (uint32_t)par);
+    double ss = 0, noise = 0, sigma1 = 0;
+    if (tid < C) { ss = auxs[C_SS]; noise = auxs[C_NOISE]; sigma1 = auxs[C_SIGMA1]; }
+    phase_a_dispatch<C>(auxs, aux_u_off, L.dpad, ng, L.d, xt, Kc, pvp, xipp, tid);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(aux_empty);
+    compute_bar_sync();
+
+    // ---- phase B: T = L^-1 Kc on the FP64 tensor pipe ----
+    double acc[RT][CT][2];
+#pragma unroll
+    for (int t = 0; t < RT; t++)
+#pragma unroll
+      for (int ct = 0; ct < CT; ct++) { acc[t][ct][0] = 0.0; acc[t][ct][1] = 0.0; }
+
+    for (int q = 0; q < a.nchunks; q++, it++) {
+      const uint32_t st = it % (uint32_t)a.stages, round = it / (uint32_t)a.stages;
+      mbar_wait(&full[st], round & 1);
+      const double* mb = ring + (size_t)st * a.chunk_max + lane;
+      const int g0 = a.chunk_g0[q], g1 = a.chunk_g0[q + 1];
+      for (int g = g0; g < g1; g++) {
+        const int r0 = g >> 1;
+        double b[CT];
+        const double* kb = Kc + ((size_t)g * C + cbase) * 4 + lane;
+#pragma unroll
+        for (int ct = 0; ct < CT; ct++) b[ct] = kb[ct * 32];
+#pragma unroll
+        for (int t = 0; t < RT; t++) {
+          const int R = tiles[t];
+          if (R >= r0) {  // tiles[] holds -1 for unused slots; live iff 8R+7 >= 4g
+            const double av = mb[(R - r0) * 32];
+#pragma unroll
+            for (int ct = 0; ct < CT; ct++) dmma884(acc[t][ct][0], acc[t][ct][1], av, b[ct]);
+          }
+        }
+        mb += (nrt - r0) * 32;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[st]);
+    }
+
+    // ---- column sums of squares over this warp's rows -> red[rg][c] ----
+#pragma unroll
+    for (int ct = 0; ct < CT; ct++) {
+      double p0 = 0.0, p1 = 0.0;
+#pragma unroll
+      for (int t = 0; t < RT; t++) {
+        p0 = fma(acc[t][ct][0], acc[t][ct][0], p0);
+        p1 = fma(acc[t][ct][1], acc[t][ct][1], p1);
+      }
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        p0 += __shfl_xor_sync(0xffffffffu, p0, o);
+        p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+      }
+      if (lane < 4) {
+        red[rg * C + cbase + ct * 8 + 2 * lane] = p0;
+        red[rg * C + cbase + ct * 8 + 2 * lane + 1] = p1;
+      }
+    }
+    compute_bar_sync();
+
+    // ---- K4 epilogue: one thread per candidate ----
+    if (tid < C) {
+      constexpr int NJQ = kComputeThreads / C;
+      const double tt = ((red[tid] + red[C + tid]) + red[2 * C + tid]) + red[3 * C + tid];
+      double wk = 0.0, xf = 1.0;
+#pragma unroll
+      for (int j = 0; j < NJQ; j++) { wk += pvp[j * C + tid]; xf *= xipp[j * C + tid]; }
+      const double xi = ss * xf;
+      const double sigma_x = ss - tt;  // latent predictive variance (GPy predict, full_cov 1x1)
+      double outv;
+      if (a.mode == kModeVariance) {
+        outv = sigma_x;
+      } else {
+        const double v = xi - wk;            // _sampler.py:399
+        const double v2 = v * v;             // :401
+        const double kxx = sigma_x + noise;  // :397 predict(include_likelihood=True)
+        const double sigma2 = sigma1 - v2 / kxx;  // :400
+        double kld;
+        if (a.form == kFormLog1p) {
+          kld = -0.5 * log1p(-(v2 / (sigma1 * kxx)));
+        } else {
+          // :480, same operation order as the reference expression
+          kld = ((log(sqrt(sigma1) / sqrt(sigma2)) + (sigma2 / (2.0 * sigma1))) + ((v2 / sigma1) / (sigma_x + noise)) * 0.5) - 0.5;
+        }
+        outv = log(kld);  // :492 np.log(kld_j)
+      }
+      if (c0 + tid < a.Nd) a.logk[(size_t)s * a.Nd + c0 + tid] = outv;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Reduction over hyper-samples (sequential in s, like the oracle) + block argmax
+// ----------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool better(double av, int64_t ai, double bv, int64_t bi) {
+  // np.argmax semantics: NaN counts as the maximum; ties -> lowest index
+  const bool an = isnan(av), bn = isnan(bv);
+  if (an || bn) {
+    if (an && bn) return ai < bi;
+    return an;
+  }
+  if (av > bv) return true;
+  if (av < bv) return false;
+  return ai < bi;
+}
+
+__global__ void __launch_bounds__(256) k_reduce(const double* __restrict__ logk, int S, int64_t Nd, int64_t idx_offset,
+                                                double* __restrict__ score, double* __restrict__ var,
+                                                double* __restrict__ part_val, int64_t* __restrict__ part_idx) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double bv = -INFINITY;
+  int64_t bi = INT64_MAX;
+  if (c < Nd) {
+    double acc = 0.0;
+    for (int s = 0; s < S; s++) acc += logk[(size_t)s * Nd + c];
+    const double mean = acc / (double)S;
+    score[c] = mean;
+    if (var != nullptr) {
+      double a2 = 0.0;
+      for (int s = 0; s < S; s++) {
+        const double dl = logk[(size_t)s * Nd + c] - mean;
+        a2 += dl * dl;
+      }
+      var[c] = a2 / (double)S;
+    }
+    bv = mean;
+    bi = idx_offset + c;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+  }
+  __shared__ double sv[8];
+  __shared__ int64_t si[8];
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; w++)
+      if (better(sv[w], si[w], bv, bi)) { bv = sv[w]; bi = si[w]; }
+    part_val[blockIdx.x] = bv;
+    part_idx[blockIdx.x] = bi;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_final_argmax(const double* __restrict__ part_val, const int64_t* __restrict__ part_idx,
+                                                      int nparts, double* __restrict__ best, int64_t* __restrict__ best_idx) {
+  double bv = -INFINITY;
+  int64_t bi = INT64_MAX;
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x)
+    if (better(part_val[i], part_idx[i], bv, bi)) { bv = part_val[i]; bi = part_idx[i]; }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+  }
+  __shared__ double sv[8];
+  __shared__ int64_t si[8];
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; w++)
+      if (better(sv[w], si[w], bv, bi)) { bv = sv[w]; bi = si[w]; }
+    best[0] = bv;
+    best_idx[0] = bi;
+  }
+}
+
+// logk -> EKLD values (for callers that want the (S, Nd) matrix the reference would have produced)
+__global__ void k_exp_inplace(double* __restrict__ v, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = exp(v[i]);
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Host-side planning and launch
+// ----------------------------------------------------------------------------------------------------------------
+static size_t score_smem_bytes(const Layout& L, int C, int stages, int chunk_max) {
+  size_t dbl = (size_t)L.npad * C + L.aux_doubles + (size_t)stages * chunk_max + 4 * C + 4 * kComputeThreads + (size_t)C * kXtStride;
+  return dbl * sizeof(double) + sizeof(uint64_t) * (2 * kMaxStages + 2) + 128;
+}
+
+// Longest-processing-time assignment of row tiles (weight R+1 = number of live k4-group pairs) to the 4 row groups.
+static void assign_tiles(int nrt, int rt_cap, short* tile_id /*[4][kMaxRT]*/) {
+  int load[4] = {0, 0, 0, 0}, cnt[4] = {0, 0, 0, 0};
+  short tmp[4][kMaxRT];
+  for (int R = nrt - 1; R >= 0; R--) {
+    int best = -1;
+    for (int g = 0; g < 4; g++)
+      if (cnt[g] < rt_cap && (best < 0 || load[g] < load[best])) best = g;
+    tmp[best][cnt[best]++] = (short)R;
+    load[best] += R + 1;
+  }
+  for (int g = 0; g < 4; g++) {
+    for (int t = 0; t < kMaxRT; t++) tile_id[g * kMaxRT + t] = -1;
+    // ascending R inside the group
+    for (int t = 0; t < cnt[g]; t++) tile_id[g * kMaxRT + t] = tmp[g][cnt[g] - 1 - t];
+  }
+}
+
+int plan_score(const Layout& L, int64_t Nd, int sm_count, size_t smem_optin, ScorePlan* P) {
+  const int nrt = L.nrt;
+  int rt, ct;
+  if (nrt <= 4 * 8) { rt = 8; ct = 4; }
+  else if (nrt <= 4 * 16) { rt = 16; ct = 2; }
+  else if (nrt <= 4 * 32) { rt = 32; ct = 1; }
+  else return -1;
+  P->rt = rt; P->ct = ct;
+  const int C = 16 * ct;
+  P->C = C;
+  // chunk plan: consecutive k4 groups, greedily packed up to the chunk size
+  const size_t g0_doubles = (size_t)nrt * 32;
+  size_t chunk_max = 2048;  // 16 KB
+  if (chunk_max < g0_doubles) chunk_max = g0_doubles;
+  int nch = 0;
+  int g = 0;
+  P->chunk_g0[0] = 0;
+  while (g < L.ng) {
+    size_t acc = 0;
+    int g1 = g;
+    while (g1 < L.ng) {
+      const size_t gs = (size_t)(nrt - (g1 >> 1)) * 32;
+      if (acc + gs > chunk_max && g1 > g) break;
+      acc += gs;
+      g1++;
+    }
+    g = g1;
+    P->chunk_g0[++nch] = (unsigned short)g;
+    if (nch >= kMaxChunks) { if (g < L.ng) return -1; break; }
+  }
+  P->nchunks = nch;
+  P->chunk_max = (int)chunk_max;
+  int stages = kMaxStages;
+  while (stages >= 2 && score_smem_bytes(L, C, stages, (int)chunk_max) > smem_optin) stages--;
+  if (stages < 2) return -1;
+  if (stages > nch + 1 && nch + 1 >= 2) stages = nch + 1;
+  P->stages = stages;
+  P->smem = score_smem_bytes(L, C, stages, (int)chunk_max);
+  assign_tiles(nrt, rt, P->tile_id);
+  // work items: (tile, sample chunk); aim for >= 16 waves of CTAs, keep at least 4 samples per item when possible
+  const int64_t ntiles = (Nd + C - 1) / C;
+  int sc = L.S;
+  const int64_t target = (int64_t)16 * sm_count;
+  while (sc > 4 && ntiles * ((L.S + sc - 1) / sc) < target) sc = (sc + 1) / 2;
+  if (ntiles * ((L.S + sc - 1) / sc) < sm_count) {
+    while (sc > 1 && ntiles * ((L.S + sc - 1) / sc) < sm_count) sc = (sc + 1) / 2;
+  }
+  P->sc = sc;
+  P->ntiles = (int)ntiles;
+  P->nitems = ntiles * ((L.S + sc - 1) / sc);
+  return 0;
+}
+
+template <int RT, int CT>
+static cudaError_t launch_one(const ScoreArgs& a, const ScorePlan& P, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(k_score<RT, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem);
+  if (e != cudaSuccess) return e;
+  k_score<RT, CT><<<(unsigned)P.nitems, kScoreThreads, P.smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_score(const ScoreArgs& a, const ScorePlan& P, cudaStream_t st) {
+  if (P.rt == 8) return launch_one<8, 4>(a, P, st);
+  if (P.rt == 16) return launch_one<16, 2>(a, P, st);
+  return launch_one<32, 1>(a, P, st);
+}
+
+cudaError_t launch_reduce(const double* logk, int S, int64_t Nd, int64_t idx_offset, double* score, double* var,
+                          double* part_val, int64_t* part_idx, double* best, int64_t* best_idx, cudaStream_t st) {
+  const int nb = (int)((Nd + 255) / 256);
+  k_reduce<<<nb, 256, 0, st>>>(logk, S, Nd, idx_offset, score, var, part_val, part_idx);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  k_final_argmax<<<1, 256, 0, st>>>(part_val, part_idx, nb, best, best_idx);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_exp_inplace(double* v, size_t n, cudaStream_t st) {
+  k_exp_inplace<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(v, n);
+  return cudaGetLastError();
+}
+
+}  // namespace bode

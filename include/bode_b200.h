@@ -1,0 +1,115 @@
+/* bode_b200 -- C ABI of the B200-native EKLD acquisition hot path.
+ *
+ * Drop-in boundary for the reference path (piyushpandita92/bode)
+ *     KLSampler.mcmc_kld            bode/_sampler.py:483-492
+ *       -> make_mcmc_model          bode/_sampler.py:449-462   (GPy exact-GP inference per hyper-sample)
+ *       -> avg_kld_mean             bode/_sampler.py:464-481   (closed-form Gaussian EKLD)
+ *       -> get_sigma_1/get_params_2 bode/_sampler.py:404-410, 391-402
+ *       -> xik / bk                 bode/_core.py:86-101
+ *     KLSampler.get_mu_sigma        bode/_sampler.py:434-444   (Q-posterior summary, by-product of prepare)
+ * The reference has no FFI (pure Python on GPy); these entry points are what a ctypes binding inside
+ * `KLSampler.mcmc_kld` / `get_mu_sigma` would call.
+ *
+ * Conventions
+ *   - plain C, no torch types.  All arrays are FP64, row-major (NumPy C order).
+ *   - `*_dev` entry points take DEVICE pointers and a `cudaStream_t` passed as `void*`; they never allocate,
+ *     never synchronise and never touch the host.  `*_host` entry points take HOST pointers, allocate device
+ *     scratch internally and synchronise before returning.
+ *   - hyper-sample layout is the reference's (`_sampler.py:273-274, 455-461`): `hyp[S][ndim]`, row =
+ *     [variance, ell_1..ell_d] (ndim == d+1, noise variance = nugget_var) or
+ *     [variance, ell_1..ell_d, noise_std] (ndim == d+2, noise variance = noise_std^2).
+ *   - every function returns 0 on success or a negative `bode_status`; nothing throws across the ABI.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns BODE_ERR_CUDA.
+ */
+#ifndef BODE_B200_H_
+#define BODE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum bode_status {
+  BODE_OK = 0,
+  BODE_ERR_BAD_ARG = -1,     /* null pointer, non-positive size, ndim not in {d+1, d+2} */
+  BODE_ERR_UNSUPPORTED = -2, /* n > BODE_MAX_N or d > BODE_MAX_D */
+  BODE_ERR_WORKSPACE = -3,   /* workspace too small / misaligned */
+  BODE_ERR_CUDA = -4,        /* CUDA runtime error (see bode_last_cuda_error) */
+  BODE_ERR_NOT_PD = -5       /* host entry points only: a Cholesky pivot was non-positive (info[s] > 0) */
+} bode_status;
+
+#define BODE_MAX_N 1024 /* observations */
+#define BODE_MAX_D 16   /* input dimensions */
+
+/* EKLD expression: the reference's literal (uncancelled) expression `_sampler.py:480`, or the analytically
+ * identical -1/2 log1p(-v^2/(sigma_1 k_xx)) which does not lose digits for small EKLD. */
+#define BODE_FORM_REFERENCE 0
+#define BODE_FORM_LOG1P 1
+
+const char* bode_version(void);
+const char* bode_strerror(int status);
+const char* bode_last_cuda_error(void);
+
+/* Bytes of device workspace `bode_ekld_prepare_dev` needs for (n observations, d dims, S hyper-samples).
+ * Returns 0 if the shape is unsupported. 256-byte alignment required. */
+size_t bode_ekld_workspace_bytes(int n, int d, int S);
+
+/* K1 -- per-hyper-sample preparation; replaces S calls of make_mcmc_model (`_sampler.py:449-462`) plus the
+ * candidate-independent parts of get_sigma_1 / get_mu_1 (`:404-422`):
+ *   A_s = K_ARD-RBF(X, X; theta_s) + (noise_var_s + jitter) I,  L_s = chol(A_s),  M_s = L_s^-1,
+ *   e_s = xik(X),  sigma0_s = bk,  a = L^-1 e,  w_s = L^-T a,  sigma1_s = sigma0 - a.a,  mu1_s = (L^-1 Y).a,
+ *   loglik_s = 0.5(-n log 2pi - logdet A_s - Y^T A_s^-1 Y)      (GPy log_marginal, `_sampler.py:232`).
+ * X[n*d], Y[n], hyp[S*ndim], info[S] are device pointers.  info[s] = 0, or j+1 if pivot j of sample s was not
+ * positive (LAPACK dpotrf convention); such a sample yields NaN downstream.
+ * `jitter` is GPy's hidden diagonal addition (1e-8 reproduces the reference fixture). */
+int bode_ekld_prepare_dev(const double* X, const double* Y, const double* hyp, int n, int d, int S, int ndim,
+                          double nugget_var, double jitter, void* workspace, size_t workspace_bytes, int* info,
+                          void* stream);
+
+/* Per-sample by-products of prepare, device -> device: out[s*8 + {0..7}] =
+ * {variance, noise_var, sigma0, sigma1, mu1, logdet, Y^T A^-1 Y, loglik}. */
+int bode_ekld_sample_terms_dev(const void* workspace, int n, int d, int S, double* out, void* stream);
+
+/* Q-posterior summary (`get_mu_sigma`, `_sampler.py:434-444`): out[0] = mean_s mu1, out[1] = mean_s sigma1,
+ * accumulated sequentially s = 0..S-1 like the reference loop.  Device pointer. */
+int bode_ekld_mu_sigma_dev(const void* workspace, int n, int d, int S, double* out, void* stream);
+
+/* K2+K3+K4 -- dense scoring; replaces Nd calls of mcmc_kld (`_sampler.py:483-492`):
+ *   logk[s*Nd + c] = log EKLD_s(X_design[c])                    (always written; scratch of S*Nd doubles)
+ *   score[c] = (1/S) sum_s logk[s][c]  (sequential in s),  var[c] = (1/S) sum_s (logk[s][c]-score[c])^2 (nullable)
+ *   best[0] = max score (NaN counts as largest, like np.argmax), best_idx[0] = idx_offset + first index attaining it.
+ * `idx_offset` is the global index of X_design[0] (multi-GPU candidate sharding).
+ * `scratch` needs bode_ekld_score_scratch_bytes(Nd) bytes. */
+size_t bode_ekld_score_scratch_bytes(int64_t Nd);
+int bode_ekld_score_dev(const void* workspace, int n, int d, int S, const double* X_design, int64_t Nd,
+                        int64_t idx_offset, int form, double* logk, double* score, double* var, double* best,
+                        int64_t* best_idx, void* scratch, void* stream);
+
+/* Uncertainty-sampling comparator (`update_comp_models`, `_sampler.py:506-514`): pred_var[c] = mean_s latent
+ * predictive variance at X_grid[c]; best/best_idx as above. Reuses the scoring kernel (no v / EKLD epilogue). */
+int bode_us_variance_dev(const void* workspace, int n, int d, int S, const double* X_grid, int64_t Ng,
+                         int64_t idx_offset, double* sigx /* S*Ng scratch */, double* pred_var, double* best,
+                         int64_t* best_idx, void* scratch, void* stream);
+
+/* Host-buffer convenience wrapper: the call a non-torch caller (or the reference's Python via ctypes) makes.
+ * Copies X, Y, hyp, X_design to the device, runs prepare + score, copies results back, synchronises.
+ * score[Nd] required; var[Nd], kld[S*Nd] (EKLD values, not logs), mu_sigma[2], info[S] nullable. */
+int bode_ekld_score_host(const double* X, const double* Y, const double* hyp, int n, int d, int S, int ndim,
+                         double nugget_var, double jitter, const double* X_design, int64_t Nd, int form,
+                         double* score, double* var, double* kld, int64_t* best_idx, double* mu_sigma, int* info);
+
+/* Batched GP log marginal likelihood for the host MCMC (`lnprob` -> `get_likelihood`, `_sampler.py:221-238`):
+ * loglik[s] for each row of hyp; -inf where the Cholesky fails.  Host pointers. */
+int bode_gp_loglik_host(const double* X, const double* Y, const double* hyp, int n, int d, int S, int ndim,
+                        double nugget_var, double jitter, double* loglik);
+
+/* Measured FP64 peak of this GPU (DMMA.8x8x4 register-resident loop and DFMA loop), TFLOP/s; used by bench.py
+ * as the roofline denominator because MEASURED_PEAKS.json has no FP64 entry. */
+int bode_fp64_peak(double* dmma_tflops, double* dfma_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BODE_B200_H_ */

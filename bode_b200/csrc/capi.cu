@@ -134,7 +134,7 @@ size_t bode_ekld_score_scratch_bytes(int64_t Nd) {
 
 static int score_common(const void* workspace, int n, int d, int S, const double* Xd, int64_t Nd, int64_t idx_offset,
                         int form, int mode, double* logk, double* score, double* var, double* best, int64_t* best_idx,
-                        void* scratch, void* stream) {
+                        void* scratch, void* stream, float* kernel_ms) {
   if (!workspace || !Xd || !logk || !score || !best || !best_idx || !scratch || !shape_ok(n, d, S) || Nd < 1)
     return BODE_ERR_BAD_ARG;
   if (form != BODE_FORM_REFERENCE && form != BODE_FORM_LOG1P) return BODE_ERR_BAD_ARG;
@@ -152,11 +152,24 @@ static int score_common(const void* workspace, int n, int d, int S, const double
   memcpy(a.chunk_g0, P.chunk_g0, sizeof(a.chunk_g0));
   memcpy(a.tile_id, P.tile_id, sizeof(a.tile_id));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (kernel_ms) {
+    BODE_CUDA(cudaEventCreate(&ev0));
+    BODE_CUDA(cudaEventCreate(&ev1));
+    BODE_CUDA(cudaEventRecord(ev0, st));
+  }
   BODE_CUDA(launch_score(a, P, st));
+  if (kernel_ms) BODE_CUDA(cudaEventRecord(ev1, st));
   const size_t nb = (size_t)((Nd + 255) / 256);
   double* part_val = static_cast<double*>(scratch);
   int64_t* part_idx = reinterpret_cast<int64_t*>(static_cast<char*>(scratch) + align_up(nb * sizeof(double), 256));
   BODE_CUDA(launch_reduce(logk, S, Nd, idx_offset, score, var, part_val, part_idx, best, best_idx, st));
+  if (kernel_ms) {
+    BODE_CUDA(cudaEventSynchronize(ev1));
+    BODE_CUDA(cudaEventElapsedTime(kernel_ms, ev0, ev1));
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+  }
   return BODE_OK;
 }
 
@@ -164,14 +177,22 @@ int bode_ekld_score_dev(const void* workspace, int n, int d, int S, const double
                         int64_t idx_offset, int form, double* logk, double* score, double* var, double* best,
                         int64_t* best_idx, void* scratch, void* stream) {
   return score_common(workspace, n, d, S, X_design, Nd, idx_offset, form, kModeEkld, logk, score, var, best, best_idx,
-                      scratch, stream);
+                      scratch, stream, nullptr);
+}
+
+int bode_ekld_score_dev_timed(const void* workspace, int n, int d, int S, const double* X_design, int64_t Nd,
+                              int64_t idx_offset, int form, double* logk, double* score, double* var, double* best,
+                              int64_t* best_idx, void* scratch, void* stream, float* score_kernel_ms) {
+  if (!score_kernel_ms) return BODE_ERR_BAD_ARG;
+  return score_common(workspace, n, d, S, X_design, Nd, idx_offset, form, kModeEkld, logk, score, var, best, best_idx,
+                      scratch, stream, score_kernel_ms);
 }
 
 int bode_us_variance_dev(const void* workspace, int n, int d, int S, const double* X_grid, int64_t Ng,
                          int64_t idx_offset, double* sigx, double* pred_var, double* best, int64_t* best_idx,
                          void* scratch, void* stream) {
   return score_common(workspace, n, d, S, X_grid, Ng, idx_offset, BODE_FORM_REFERENCE, kModeVariance, sigx, pred_var,
-                      nullptr, best, best_idx, scratch, stream);
+                      nullptr, best, best_idx, scratch, stream, nullptr);
 }
 
 int bode_ekld_score_host(const double* X, const double* Y, const double* hyp, int n, int d, int S, int ndim,

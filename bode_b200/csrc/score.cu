@@ -62,7 +62,7 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32
                : "memory");
 }
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
 }
@@ -71,6 +71,29 @@ __device__ __forceinline__ void compute_bar_sync() { asm volatile("bar.sync 1, %
 // ----------------------------------------------------------------------------------------------------------------
 // Phase A: Kc[(g*C + c)*4 + kk] = ss * exp(-sum_k (U[4g+kk][k] - x_c[k] ck[k])^2); partial w.k; partial xik factors
 // ----------------------------------------------------------------------------------------------------------------
+template <int DP>
+__device__ __forceinline__ double sqdist(const double* __restrict__ uj, const double (&y)[DP]) {
+  double r2;
+  if (DP == 1) {
+    const double t = uj[0] - y[0];
+    r2 = t * t;
+  } else {
+    r2 = 0.0;
+#pragma unroll
+    for (int k2 = 0; k2 < DP / 2; k2++) {
+      const double2 u = *reinterpret_cast<const double2*>(uj + 2 * k2);
+      const double t0 = u.x - y[2 * k2], t1 = u.y - y[2 * k2 + 1];
+      r2 = fma(t0, t0, r2);
+      r2 = fma(t1, t1, r2);
+    }
+    if (DP & 1) {
+      const double t = uj[DP - 1] - y[DP - 1];
+      r2 = fma(t, t, r2);
+    }
+  }
+  return r2;
+}
+
 template <int DP, int C>
 __device__ __forceinline__ void phase_a(const double* __restrict__ aux, int aux_u_off, int dpad, int ng, int d,
                                         const double* __restrict__ xt, double* __restrict__ Kc,
@@ -84,42 +107,43 @@ __device__ __forceinline__ void phase_a(const double* __restrict__ aux, int aux_
   const double* U = aux + aux_u_off;
   double y[DP];
 #pragma unroll
-  for (int k = 0; k < DP; k++) y[k] = (k < d) ? xt[c * kXtStride + k] * ck[k] : 0.0;
+  for (int k = 0; k < DP; k++) y[k] = xt[c * kXtStride + k] * ck[k];
   double wk = 0.0;
-  for (int g = jq; g < ng; g += NJQ) {
-    double r2[4] = {0.0, 0.0, 0.0, 0.0};
+  int g = jq;
+  // two k4 groups (8 independent exp chains) per iteration
+  for (; g + NJQ < ng; g += 2 * NJQ) {
+    double r2[8];
 #pragma unroll
     for (int kk = 0; kk < 4; kk++) {
-      const double* uj = U + (size_t)(4 * g + kk) * dpad;
-      if (DP == 1) {
-        const double t = uj[0] - y[0];
-        r2[kk] = t * t;
-      } else {
-#pragma unroll
-        for (int k2 = 0; k2 < DP / 2; k2++) {
-          const double2 u = *reinterpret_cast<const double2*>(uj + 2 * k2);
-          const double t0 = u.x - y[2 * k2], t1 = u.y - y[2 * k2 + 1];
-          r2[kk] = fma(t0, t0, r2[kk]);
-          r2[kk] = fma(t1, t1, r2[kk]);
-        }
-        if (DP & 1) {
-          const double t = uj[DP - 1] - y[DP - 1];
-          r2[kk] = fma(t, t, r2[kk]);
-        }
-      }
+      r2[kk] = sqdist<DP>(U + (size_t)(4 * g + kk) * dpad, y);
+      r2[4 + kk] = sqdist<DP>(U + (size_t)(4 * (g + NJQ) + kk) * dpad, y);
     }
+    double kv[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) kv[i] = ss * exp(-r2[i]);
+    const double2 wa = *reinterpret_cast<const double2*>(w + 4 * g);
+    const double2 wb = *reinterpret_cast<const double2*>(w + 4 * g + 2);
+    const double2 wc = *reinterpret_cast<const double2*>(w + 4 * (g + NJQ));
+    const double2 wd = *reinterpret_cast<const double2*>(w + 4 * (g + NJQ) + 2);
+    wk = fma(wa.x, kv[0], wk); wk = fma(wa.y, kv[1], wk); wk = fma(wb.x, kv[2], wk); wk = fma(wb.y, kv[3], wk);
+    wk = fma(wc.x, kv[4], wk); wk = fma(wc.y, kv[5], wk); wk = fma(wd.x, kv[6], wk); wk = fma(wd.y, kv[7], wk);
+    double2* d0 = reinterpret_cast<double2*>(Kc + ((size_t)g * C + c) * 4);
+    d0[0] = make_double2(kv[0], kv[1]);
+    d0[1] = make_double2(kv[2], kv[3]);
+    double2* d1 = reinterpret_cast<double2*>(Kc + ((size_t)(g + NJQ) * C + c) * 4);
+    d1[0] = make_double2(kv[4], kv[5]);
+    d1[1] = make_double2(kv[6], kv[7]);
+  }
+  if (g < ng) {
     double kv[4];
 #pragma unroll
-    for (int kk = 0; kk < 4; kk++) kv[kk] = ss * exp(-r2[kk]);
-    const double2 w01 = *reinterpret_cast<const double2*>(w + 4 * g);
-    const double2 w23 = *reinterpret_cast<const double2*>(w + 4 * g + 2);
-    wk = fma(w01.x, kv[0], wk);
-    wk = fma(w01.y, kv[1], wk);
-    wk = fma(w23.x, kv[2], wk);
-    wk = fma(w23.y, kv[3], wk);
-    double2* dst = reinterpret_cast<double2*>(Kc + ((size_t)g * C + c) * 4);
-    dst[0] = make_double2(kv[0], kv[1]);
-    dst[1] = make_double2(kv[2], kv[3]);
+    for (int kk = 0; kk < 4; kk++) kv[kk] = ss * exp(-sqdist<DP>(U + (size_t)(4 * g + kk) * dpad, y));
+    const double2 wa = *reinterpret_cast<const double2*>(w + 4 * g);
+    const double2 wb = *reinterpret_cast<const double2*>(w + 4 * g + 2);
+    wk = fma(wa.x, kv[0], wk); wk = fma(wa.y, kv[1], wk); wk = fma(wb.x, kv[2], wk); wk = fma(wb.y, kv[3], wk);
+    double2* d0 = reinterpret_cast<double2*>(Kc + ((size_t)g * C + c) * 4);
+    d0[0] = make_double2(kv[0], kv[1]);
+    d0[1] = make_double2(kv[2], kv[3]);
   }
   pv[jq * C + c] = wk;
   // xik factors of the dimensions k == jq (mod NJQ): sqrt(pi)/sqrt(2) * ell_k * (erf((1-x) ck) - erf((0-x) ck))
@@ -148,11 +172,53 @@ __device__ __forceinline__ void phase_a_dispatch(const double* aux, int aux_u_of
 }
 
 // ----------------------------------------------------------------------------------------------------------------
-// The scoring kernel.  RT = row tiles per warp row-group (4 row groups), CT = column tiles per warp (2 col groups).
+// Phase B inner loop: k4 groups [g, g_end) during which exactly the accumulator slots T0..RT-1 are live.
+// All fragment loads of a group are issued before its DMMAs (no predicates, no per-slot branches).
 // ----------------------------------------------------------------------------------------------------------------
+template <int RT, int CT, int T0>
+__device__ __forceinline__ void run_groups(double (&acc)[RT][CT][2], const int (&tiles)[RT], const double* __restrict__ kc_lane,
+                                           const double* __restrict__ chunk_lane, size_t chunk_off0, int g, int g_end,
+                                           int C, int nrt) {
+#pragma unroll 2
+  for (; g < g_end; ++g) {
+    const int r0 = g >> 1;
+    const double* mb = chunk_lane + (m_goff(nrt, g) - chunk_off0);
+    const double* kb = kc_lane + (size_t)g * C * 4;
+    double b[CT], a[RT - T0];
+#pragma unroll
+    for (int ct = 0; ct < CT; ct++) b[ct] = kb[ct * 32];
+#pragma unroll
+    for (int t = T0; t < RT; t++) a[t - T0] = mb[(tiles[t] - r0) * 32];
+#pragma unroll
+    for (int t = T0; t < RT; t++)
+#pragma unroll
+      for (int ct = 0; ct < CT; ct++) dmma884(acc[t][ct][0], acc[t][ct][1], a[t - T0], b[ct]);
+  }
+}
+
+template <int RT, int CT, int T0 = 0>
+struct SegDispatch {
+  static __device__ __forceinline__ void run(int t0, double (&acc)[RT][CT][2], const int (&tiles)[RT], const double* kc_lane,
+                                             const double* chunk_lane, size_t chunk_off0, int g, int g_end, int C, int nrt) {
+    if (t0 == T0) run_groups<RT, CT, T0>(acc, tiles, kc_lane, chunk_lane, chunk_off0, g, g_end, C, nrt);
+    else SegDispatch<RT, CT, T0 + 1>::run(t0, acc, tiles, kc_lane, chunk_lane, chunk_off0, g, g_end, C, nrt);
+  }
+};
 template <int RT, int CT>
+struct SegDispatch<RT, CT, RT> {
+  static __device__ __forceinline__ void run(int, double (&)[RT][CT][2], const int (&)[RT], const double*, const double*,
+                                             size_t, int, int, int, int) {}
+};
+
+// ----------------------------------------------------------------------------------------------------------------
+// The scoring kernel.  16 compute warps = RG row groups x CG column groups; each warp owns up to RT row tiles
+// (8 rows of T each) x CT column tiles (8 candidates each) as DMMA accumulators.  C = CG*CT*8 candidates per CTA.
+// ----------------------------------------------------------------------------------------------------------------
+template <int RG, int CG, int RT, int CT>
 __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constant__ ScoreArgs a) {
-  constexpr int C = 16 * CT;  // candidates per CTA
+  static_assert(RG * CG == kComputeWarps, "warp grid");
+  constexpr int C = CG * CT * 8;  // candidates per CTA
+  constexpr int NJQ = kComputeThreads / C;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const Layout& L = a.L;
@@ -162,8 +228,8 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
   double* Kc = reinterpret_cast<double*>(smem_raw);             // [ng][C][4]
   double* auxs = Kc + (size_t)npad * C;                          // aux block of the current sample
   double* ring = auxs + L.aux_doubles;                           // [stages][chunk_max]
-  double* red = ring + (size_t)a.stages * a.chunk_max;           // [4][C]
-  double* pv = red + 4 * C;                                      // [2][NJQ][C]   (NJQ*C = 256)
+  double* red = ring + (size_t)a.stages * a.chunk_max;           // [RG][C]
+  double* pv = red + RG * C;                                     // [2][NJQ][C]   (NJQ*C = kComputeThreads)
   double* xip = pv + 2 * kComputeThreads;                        // [2][NJQ][C]
   double* xt = xip + 2 * kComputeThreads;                        // [C][kXtStride]
   uint64_t* bars = reinterpret_cast<uint64_t*>(xt + C * kXtStride);
@@ -171,6 +237,7 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
   uint64_t* empty = bars + kMaxStages;    // [stages]
   uint64_t* aux_full = bars + 2 * kMaxStages;
   uint64_t* aux_empty = aux_full + 1;
+  int* seg_end = reinterpret_cast<int*>(aux_empty + 1);  // [RG][RT+1]: k4 group at which slot t dies
 
   // ---- work item ----
   const int item = blockIdx.x;
@@ -187,6 +254,10 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
     mbar_init(aux_empty, kComputeWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (tid < RG * (RT + 1)) {
+    const int r = tid / (RT + 1), t = tid - r * (RT + 1);
+    seg_end[tid] = (t < RT) ? 2 * (int)a.tile_id[r * kMaxRT + t] + 2 : 0x7fffffff;  // unused slot (-1) -> 0
+  }
   // candidate tile -> smem (rows beyond Nd are filled with a harmless interior point)
   for (int idx = tid; idx < C * kXtStride; idx += kScoreThreads) {
     const int c = idx / kXtStride, k = idx - c * kXtStride;
@@ -201,9 +272,12 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
   const double* m_g = reinterpret_cast<const double*>(wsb + L.off_m);
   const uint32_t aux_bytes = (uint32_t)(L.aux_doubles * sizeof(double));
 
-  if (warp == kComputeWarps) {
-    // ===================================== producer warp (one elected lane) =====================================
-    if (lane == 0) {
+  if (warp >= kComputeWarps) {
+    // ============================ producer warpgroup (one elected lane of its first warp) ========================
+    // Register budget: the CTA launches with 20 warps x 96 registers; this warpgroup shrinks to 24 so that the four
+    // compute warpgroups can grow to 112 out of the registers it releases (setmaxnreg is warpgroup-collective, hence a full group of 4 warps here).
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    if (warp == kComputeWarps && lane == 0) {
       uint32_t it = 0;  // running chunk counter -> ring stage / parity
       for (int s = s_begin; s < s_end; s++) {
         const int ls = s - s_begin;
@@ -225,11 +299,14 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
   }
 
   // ========================================== compute warps ======================================================
-  const int rg = warp & 3, cg = warp >> 2;
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+  const int rg = warp % RG, cg = warp / RG;
   const int cbase = cg * CT * 8;
   int tiles[RT];
 #pragma unroll
   for (int t = 0; t < RT; t++) tiles[t] = a.tile_id[rg * kMaxRT + t];
+  const int* my_seg_end = seg_end + rg * (RT + 1);
+  const double* kc_lane = Kc + (size_t)cbase * 4 + lane;
 
   const int aux_u_off = aux_u(L);
   uint32_t it = 0;
@@ -253,28 +330,21 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
 #pragma unroll
       for (int ct = 0; ct < CT; ct++) { acc[t][ct][0] = 0.0; acc[t][ct][1] = 0.0; }
 
+    int g = 0, t0 = 0;
     for (int q = 0; q < a.nchunks; q++, it++) {
       const uint32_t st = it % (uint32_t)a.stages, round = it / (uint32_t)a.stages;
       mbar_wait(&full[st], round & 1);
-      const double* mb = ring + (size_t)st * a.chunk_max + lane;
-      const int g0 = a.chunk_g0[q], g1 = a.chunk_g0[q + 1];
-      for (int g = g0; g < g1; g++) {
-        const int r0 = g >> 1;
-        double b[CT];
-        const double* kb = Kc + ((size_t)g * C + cbase) * 4 + lane;
-#pragma unroll
-        for (int ct = 0; ct < CT; ct++) b[ct] = kb[ct * 32];
-#pragma unroll
-        for (int t = 0; t < RT; t++) {
-          const int R = tiles[t];
-          if (R >= r0) {  // tiles[] holds -1 for unused slots; live iff 8R+7 >= 4g
-            const double av = mb[(R - r0) * 32];
-#pragma unroll
-            for (int ct = 0; ct < CT; ct++) dmma884(acc[t][ct][0], acc[t][ct][1], av, b[ct]);
-          }
-        }
-        mb += (nrt - r0) * 32;
+      const double* chunk_lane = ring + (size_t)st * a.chunk_max + lane;
+      const int g_hi = a.chunk_g0[q + 1];
+      const size_t chunk_off0 = m_goff(nrt, a.chunk_g0[q]);
+      while (g < g_hi) {
+        while (my_seg_end[t0] <= g) t0++;   // sentinel at [RT] stops the scan
+        if (t0 >= RT) { g = g_hi; break; }
+        const int ge = min(g_hi, my_seg_end[t0]);
+        SegDispatch<RT, CT>::run(t0, acc, tiles, kc_lane, chunk_lane, chunk_off0, g, ge, C, nrt);
+        g = ge;
       }
+      g = g_hi;
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[st]);
     }
@@ -302,8 +372,9 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
 
     // ---- K4 epilogue: one thread per candidate ----
     if (tid < C) {
-      constexpr int NJQ = kComputeThreads / C;
-      const double tt = ((red[tid] + red[C + tid]) + red[2 * C + tid]) + red[3 * C + tid];
+      double tt = red[tid];
+#pragma unroll
+      for (int r = 1; r < RG; r++) tt += red[r * C + tid];
       double wk = 0.0, xf = 1.0;
 #pragma unroll
       for (int j = 0; j < NJQ; j++) { wk += pvp[j * C + tid]; xf *= xipp[j * C + tid]; }
@@ -417,38 +488,38 @@ __global__ void k_exp_inplace(double* __restrict__ v, size_t n) {
 // ----------------------------------------------------------------------------------------------------------------
 // Host-side planning and launch
 // ----------------------------------------------------------------------------------------------------------------
-static size_t score_smem_bytes(const Layout& L, int C, int stages, int chunk_max) {
-  size_t dbl = (size_t)L.npad * C + L.aux_doubles + (size_t)stages * chunk_max + 4 * C + 4 * kComputeThreads + (size_t)C * kXtStride;
-  return dbl * sizeof(double) + sizeof(uint64_t) * (2 * kMaxStages + 2) + 128;
+static size_t score_smem_bytes(const Layout& L, int C, int RG, int stages, int chunk_max) {
+  size_t dbl = (size_t)L.npad * C + L.aux_doubles + (size_t)stages * chunk_max + (size_t)RG * C + 4 * kComputeThreads +
+               (size_t)C * kXtStride;
+  return dbl * sizeof(double) + sizeof(uint64_t) * (2 * kMaxStages + 2) + sizeof(int) * kMaxRG * (kMaxRT + 1) + 128;
 }
 
-// Longest-processing-time assignment of row tiles (weight R+1 = number of live k4-group pairs) to the 4 row groups.
-static void assign_tiles(int nrt, int rt_cap, short* tile_id /*[4][kMaxRT]*/) {
-  int load[4] = {0, 0, 0, 0}, cnt[4] = {0, 0, 0, 0};
-  short tmp[4][kMaxRT];
+// Longest-processing-time assignment of row tiles (weight R+1 ~ number of live k4 groups) to the row groups.
+// Inside a group the tiles are stored ascending and right-aligned: slots [RT-cnt, RT), unused slots = -1.
+static void assign_tiles(int nrt, int nrg, int rt_cap, short* tile_id /*[kMaxRG][kMaxRT]*/) {
+  int load[kMaxRG], cnt[kMaxRG];
+  short tmp[kMaxRG][kMaxRT];
+  for (int g = 0; g < nrg; g++) { load[g] = 0; cnt[g] = 0; }
   for (int R = nrt - 1; R >= 0; R--) {
     int best = -1;
-    for (int g = 0; g < 4; g++)
+    for (int g = 0; g < nrg; g++)
       if (cnt[g] < rt_cap && (best < 0 || load[g] < load[best])) best = g;
-    tmp[best][cnt[best]++] = (short)R;
+    tmp[best][cnt[best]++] = (short)R;  // descending R
     load[best] += R + 1;
   }
-  for (int g = 0; g < 4; g++) {
+  for (int g = 0; g < kMaxRG; g++)
     for (int t = 0; t < kMaxRT; t++) tile_id[g * kMaxRT + t] = -1;
-    // ascending R inside the group
-    for (int t = 0; t < cnt[g]; t++) tile_id[g * kMaxRT + t] = tmp[g][cnt[g] - 1 - t];
-  }
+  for (int g = 0; g < nrg; g++)
+    for (int t = 0; t < cnt[g]; t++) tile_id[g * kMaxRT + (rt_cap - 1 - t)] = tmp[g][t];
 }
 
 int plan_score(const Layout& L, int64_t Nd, int sm_count, size_t smem_optin, ScorePlan* P) {
   const int nrt = L.nrt;
-  int rt, ct;
-  if (nrt <= 4 * 8) { rt = 8; ct = 4; }
-  else if (nrt <= 4 * 16) { rt = 16; ct = 2; }
-  else if (nrt <= 4 * 32) { rt = 32; ct = 1; }
+  if (nrt <= 32) { P->variant = 0; P->rg = 4; P->cg = 4; P->rt = 8; P->ct = 2; }
+  else if (nrt <= 64) { P->variant = 1; P->rg = 4; P->cg = 4; P->rt = 16; P->ct = 1; }
+  else if (nrt <= 128) { P->variant = 2; P->rg = 8; P->cg = 2; P->rt = 16; P->ct = 1; }
   else return -1;
-  P->rt = rt; P->ct = ct;
-  const int C = 16 * ct;
+  const int C = P->cg * P->ct * 8;
   P->C = C;
   // chunk plan: consecutive k4 groups, greedily packed up to the chunk size
   const size_t g0_doubles = (size_t)nrt * 32;
@@ -473,12 +544,12 @@ int plan_score(const Layout& L, int64_t Nd, int sm_count, size_t smem_optin, Sco
   P->nchunks = nch;
   P->chunk_max = (int)chunk_max;
   int stages = kMaxStages;
-  while (stages >= 2 && score_smem_bytes(L, C, stages, (int)chunk_max) > smem_optin) stages--;
+  while (stages >= 2 && score_smem_bytes(L, C, P->rg, stages, (int)chunk_max) > smem_optin) stages--;
   if (stages < 2) return -1;
   if (stages > nch + 1 && nch + 1 >= 2) stages = nch + 1;
   P->stages = stages;
-  P->smem = score_smem_bytes(L, C, stages, (int)chunk_max);
-  assign_tiles(nrt, rt, P->tile_id);
+  P->smem = score_smem_bytes(L, C, P->rg, stages, (int)chunk_max);
+  assign_tiles(nrt, P->rg, P->rt, P->tile_id);
   // work items: (tile, sample chunk); aim for >= 16 waves of CTAs, keep at least 4 samples per item when possible
   const int64_t ntiles = (Nd + C - 1) / C;
   int sc = L.S;
@@ -493,18 +564,18 @@ int plan_score(const Layout& L, int64_t Nd, int sm_count, size_t smem_optin, Sco
   return 0;
 }
 
-template <int RT, int CT>
+template <int RG, int CG, int RT, int CT>
 static cudaError_t launch_one(const ScoreArgs& a, const ScorePlan& P, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(k_score<RT, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem);
+  cudaError_t e = cudaFuncSetAttribute(k_score<RG, CG, RT, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem);
   if (e != cudaSuccess) return e;
-  k_score<RT, CT><<<(unsigned)P.nitems, kScoreThreads, P.smem, st>>>(a);
+  k_score<RG, CG, RT, CT><<<(unsigned)P.nitems, kScoreThreads, P.smem, st>>>(a);
   return cudaGetLastError();
 }
 
 cudaError_t launch_score(const ScoreArgs& a, const ScorePlan& P, cudaStream_t st) {
-  if (P.rt == 8) return launch_one<8, 4>(a, P, st);
-  if (P.rt == 16) return launch_one<16, 2>(a, P, st);
-  return launch_one<32, 1>(a, P, st);
+  if (P.variant == 0) return launch_one<4, 4, 8, 2>(a, P, st);
+  if (P.variant == 1) return launch_one<4, 4, 16, 1>(a, P, st);
+  return launch_one<8, 2, 16, 1>(a, P, st);
 }
 
 cudaError_t launch_reduce(const double* logk, int S, int64_t Nd, int64_t idx_offset, double* score, double* var,

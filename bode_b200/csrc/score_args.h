@@ -7,11 +7,12 @@
 
 namespace bode {
 
-constexpr int kComputeWarps = 8;
-constexpr int kComputeThreads = kComputeWarps * 32;  // 256
-constexpr int kScoreThreads = kComputeThreads + 32;  // + one producer warp
+constexpr int kComputeWarps = 16;
+constexpr int kComputeThreads = kComputeWarps * 32;  // 512
+constexpr int kScoreThreads = kComputeThreads + 128;  // + one producer warpgroup (1 active warp)
 constexpr int kMaxStages = 8;
-constexpr int kMaxRT = 32;      // row tiles per warp row-group (n <= 1024)
+constexpr int kMaxRT = 16;      // row tiles per warp row-group
+constexpr int kMaxRG = 8;       // row groups
 constexpr int kMaxChunks = 256;
 constexpr int kXtStride = 16;   // BODE_MAX_D doubles per candidate row in shared memory
 constexpr int kModeEkld = 0, kModeVariance = 1;
@@ -29,17 +30,18 @@ struct ScoreArgs {
   int form, mode;
   int stages, chunk_max /* doubles */, nchunks;
   unsigned short chunk_g0[kMaxChunks + 1];
-  short tile_id[4 * kMaxRT];
+  short tile_id[kMaxRG * kMaxRT];  // [rg][slot], right-aligned ascending, -1 = unused
 };
 
 struct ScorePlan {
-  int rt, ct, C;
+  int variant;  // 0: n<=256 (RG4 CG4 RT8 CT2), 1: n<=512 (RG4 CG4 RT16 CT1), 2: n<=1024 (RG8 CG2 RT16 CT1)
+  int rg, cg, rt, ct, C;
   int sc, ntiles;
   int64_t nitems;
   int stages, chunk_max, nchunks;
   size_t smem;
   unsigned short chunk_g0[kMaxChunks + 1];
-  short tile_id[4 * kMaxRT];
+  short tile_id[kMaxRG * kMaxRT];
 };
 
 }  // namespace bode

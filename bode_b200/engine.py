@@ -1,0 +1,166 @@
+"""Device-resident front end of the EKLD hot path: torch tensors in HBM -> C ABI (``*_dev`` entry points).
+
+``EkldEngine`` owns the per-iteration device state that replaces the reference's per-(candidate, sample) GPy
+objects (``make_mcmc_model``, ``_sampler.py:449-462``): one workspace holding, for every hyper-sample, the
+Cholesky-derived factors the scoring kernel streams.  PyTorch is plumbing only (allocation, streams, H2D/D2H).
+
+No CPU fallback: constructing an engine without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _ext
+
+GPY_JITTER = 1e-8  # GPy ExactGaussianInference adds 1e-8 to the diagonal (fixture-verified, see oracle/)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class EkldEngine:
+    """prepare(X, Y, hyp) once per outer iteration, then score(X_design) / us_variance(X_grid) / mu_sigma()."""
+
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("bode_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _ext.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.n = self.d = self.S = 0
+        self.ws = None
+        self.info = None
+        self._scratch = {}
+        self.last_kernel_ms = None
+
+    # ---- helpers -------------------------------------------------------------------------------------------
+    def _dev(self, a, shape=None):
+        if isinstance(a, torch.Tensor):
+            t = a.to(device=self.device, dtype=torch.float64).contiguous()
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.device, non_blocking=True)
+        if shape is not None:
+            t = t.reshape(shape)
+        return t
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _buf(self, name, numel, dtype):
+        t = self._scratch.get(name)
+        if t is None or t.numel() < numel or t.dtype != dtype:
+            t = torch.empty(int(numel), dtype=dtype, device=self.device)
+            self._scratch[name] = t
+        return t
+
+    # ---- K1 ------------------------------------------------------------------------------------------------
+    def prepare(self, X, Y, hyp, nugget_var, jitter=GPY_JITTER):
+        """Factorise every hyper-sample (``bode_ekld_prepare_dev``).  hyp: (S, d+1) or (S, d+2) reference layout."""
+        with torch.cuda.device(self.device):
+            Xd = self._dev(X)
+            n, d = Xd.shape
+            Yd = self._dev(Y).reshape(-1)
+            if Yd.numel() != n:
+                raise ValueError("Y must have one row per observation")
+            H = self._dev(hyp)
+            if H.dim() != 2:
+                raise ValueError("hyp must be 2-D (S, d+1 | d+2)")
+            S, ndim = H.shape
+            nbytes = self.lib.bode_ekld_workspace_bytes(n, d, S)
+            if nbytes == 0:
+                _ext.check(-2)
+            if self.ws is None or self.ws.numel() < nbytes:
+                self.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self.info = self._buf("info", S, torch.int32)[:S]
+            _ext.check(self.lib.bode_ekld_prepare_dev(_ptr(Xd), _ptr(Yd), _ptr(H), n, d, S, ndim, float(nugget_var),
+                                                      float(jitter), _ptr(self.ws), self.ws.numel(), _ptr(self.info),
+                                                      self._stream()))
+            self.n, self.d, self.S = n, d, S
+            self._keep = (Xd, Yd, H)  # keep inputs alive until the stream has consumed them
+        return self.info
+
+    def sample_terms(self):
+        """(S, 8) device tensor: variance, noise_var, sigma0, sigma1, mu1, logdet, Y^T A^-1 Y, loglik."""
+        with torch.cuda.device(self.device):
+            out = torch.empty((self.S, 8), dtype=torch.float64, device=self.device)
+            _ext.check(self.lib.bode_ekld_sample_terms_dev(_ptr(self.ws), self.n, self.d, self.S, _ptr(out), self._stream()))
+        return out
+
+    def mu_sigma(self):
+        """``get_mu_sigma`` (``_sampler.py:434-444``): (mean_s mu_1, mean_s sigma_1) as Python floats."""
+        with torch.cuda.device(self.device):
+            out = torch.empty(2, dtype=torch.float64, device=self.device)
+            _ext.check(self.lib.bode_ekld_mu_sigma_dev(_ptr(self.ws), self.n, self.d, self.S, _ptr(out), self._stream()))
+            mu, sg = out.cpu().tolist()
+        return mu, sg
+
+    # ---- K2-K4 ---------------------------------------------------------------------------------------------
+    def score(self, X_design, idx_offset=0, form=_ext.BODE_FORM_REFERENCE, want_var=True, timed=False):
+        """Score every row of X_design (device or host array).  Returns device tensors:
+        dict(score (Nd,), var (Nd,)|None, logk (S, Nd), best (1,), best_idx (1,) int64)."""
+        if self.ws is None:
+            raise RuntimeError("call prepare() first")
+        with torch.cuda.device(self.device):
+            Xd = self._dev(X_design)
+            if Xd.dim() == 1:
+                Xd = Xd.reshape(1, -1)
+            Nd, d = Xd.shape
+            if d != self.d:
+                raise ValueError("X_design has %d columns, observations have %d" % (d, self.d))
+            logk = self._buf("logk", self.S * Nd, torch.float64)[: self.S * Nd].view(self.S, Nd)
+            score = torch.empty(Nd, dtype=torch.float64, device=self.device)
+            var = torch.empty(Nd, dtype=torch.float64, device=self.device) if want_var else None
+            best = torch.empty(1, dtype=torch.float64, device=self.device)
+            best_idx = torch.empty(1, dtype=torch.int64, device=self.device)
+            scr = self._buf("scratch", self.lib.bode_ekld_score_scratch_bytes(Nd), torch.uint8)
+            args = [_ptr(self.ws), self.n, self.d, self.S, _ptr(Xd), Nd, int(idx_offset), int(form), _ptr(logk),
+                    _ptr(score), _ptr(var), _ptr(best), _ptr(best_idx), _ptr(scr), self._stream()]
+            if timed:
+                ms = ctypes.c_float(0.0)
+                _ext.check(self.lib.bode_ekld_score_dev_timed(*args, ctypes.c_void_p(ctypes.addressof(ms))))
+                self.last_kernel_ms = ms.value
+            else:
+                _ext.check(self.lib.bode_ekld_score_dev(*args))
+            self._keep_x = Xd
+        return dict(score=score, var=var, logk=logk, best=best, best_idx=best_idx)
+
+    def us_variance(self, X_grid, idx_offset=0):
+        """Uncertainty-sampling comparator (``_sampler.py:506-514``): mean_s latent predictive variance + argmax."""
+        if self.ws is None:
+            raise RuntimeError("call prepare() first")
+        with torch.cuda.device(self.device):
+            Xg = self._dev(X_grid)
+            Ng, d = Xg.shape
+            if d != self.d:
+                raise ValueError("X_grid has %d columns, observations have %d" % (d, self.d))
+            sigx = self._buf("logk", self.S * Ng, torch.float64)[: self.S * Ng].view(self.S, Ng)
+            pv = torch.empty(Ng, dtype=torch.float64, device=self.device)
+            best = torch.empty(1, dtype=torch.float64, device=self.device)
+            best_idx = torch.empty(1, dtype=torch.int64, device=self.device)
+            scr = self._buf("scratch", self.lib.bode_ekld_score_scratch_bytes(Ng), torch.uint8)
+            _ext.check(self.lib.bode_us_variance_dev(_ptr(self.ws), self.n, self.d, self.S, _ptr(Xg), Ng, int(idx_offset),
+                                                     _ptr(sigx), _ptr(pv), _ptr(best), _ptr(best_idx), _ptr(scr),
+                                                     self._stream()))
+            self._keep_x = Xg
+        return dict(pred_var=pv, sigma_x=sigx, best=best, best_idx=best_idx)
+
+
+def ekld_score(X, Y, hyp, X_design, nugget=1e-3, jitter=GPY_JITTER, form=_ext.BODE_FORM_REFERENCE, engine=None,
+               want_kld=False):
+    """One-call public API with host (NumPy) buffers: prepare + score + summary, results back on the host.
+
+    Returns dict(score, var, argmax, best, mu_Q, sigma_Q, info[, kld]).  This is the dense generalisation of
+    ``KLSampler.mcmc_kld`` (``_sampler.py:483-492``) over all rows of ``X_design``.
+    """
+    eng = EkldEngine() if engine is None else engine
+    info = eng.prepare(X, Y, hyp, nugget ** 2, jitter)
+    r = eng.score(X_design, form=form)
+    mu, sg = eng.mu_sigma()
+    out = dict(score=r["score"].cpu().numpy(), var=r["var"].cpu().numpy(), argmax=int(r["best_idx"].item()),
+               best=float(r["best"].item()), mu_Q=mu, sigma_Q=sg, info=info.cpu().numpy())
+    if want_kld:
+        out["kld"] = torch.exp(r["logk"]).cpu().numpy()
+    return out

@@ -87,6 +87,13 @@ int bode_ekld_score_dev(const void* workspace, int n, int d, int S, const double
                         int64_t idx_offset, int form, double* logk, double* score, double* var, double* best,
                         int64_t* best_idx, void* scratch, void* stream);
 
+/* Same as bode_ekld_score_dev, and additionally times the dominant kernel (the fused K2-K4 scoring kernel) with
+ * CUDA events recorded on `stream`; synchronises on the stop event before returning.  Used by bench.py for the
+ * roofline figure. */
+int bode_ekld_score_dev_timed(const void* workspace, int n, int d, int S, const double* X_design, int64_t Nd,
+                              int64_t idx_offset, int form, double* logk, double* score, double* var, double* best,
+                              int64_t* best_idx, void* scratch, void* stream, float* score_kernel_ms);
+
 /* Uncertainty-sampling comparator (`update_comp_models`, `_sampler.py:506-514`): pred_var[c] = mean_s latent
  * predictive variance at X_grid[c]; best/best_idx as above. Reuses the scoring kernel (no v / EKLD epilogue). */
 int bode_us_variance_dev(const void* workspace, int n, int d, int S, const double* X_grid, int64_t Ng,

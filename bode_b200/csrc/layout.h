@@ -5,6 +5,7 @@
 //                consts[8]  = {variance, noise_var, sigma0, sigma1, mu1, logdet, Y^T A^-1 Y, loglik}
 //                ck[16]     = 1/(sqrt(2) ell_k)            (zero padded)
 //                ell[16]    = ell_k                        (one padded)
+//                tab[32]    = variance * 2^(j/32)         (table of rbf_exp, see rbf.h)
 //                w[npad]    = A^-1 e                       (zero padded)
 //                U[npad][dpad] = X[j][k] * ck[k]           (zero padded rows / columns)
 //   M[s]     : L_s^-1 in the "k4-group major, live row-tile suffix" tiling the DMMA mainloop consumes:
@@ -27,6 +28,7 @@ namespace bode {
 
 constexpr int kConsts = 8;
 constexpr int kCkPad = 16;
+constexpr int kTabPad = 32;
 enum ConstIdx { C_SS = 0, C_NOISE = 1, C_SIGMA0 = 2, C_SIGMA1 = 3, C_MU1 = 4, C_LOGDET = 5, C_QUAD = 6, C_LOGLIK = 7 };
 
 struct Layout {
@@ -51,7 +53,7 @@ BODE_HD Layout make_layout(int n, int d, int S) {
   L.npad = 8 * L.nrt;
   L.ng = 2 * L.nrt;
   L.dpad = (d + 1) & ~1;
-  L.aux_doubles = (size_t)kConsts + 2 * kCkPad + L.npad + (size_t)L.npad * L.dpad;
+  L.aux_doubles = (size_t)kConsts + 2 * kCkPad + kTabPad + L.npad + (size_t)L.npad * L.dpad;
   L.m_doubles = (size_t)32 * L.nrt * (L.nrt + 1);
   L.lw_doubles = (size_t)(n + 2) * L.npad;
   L.xw_doubles = (size_t)n * L.npad;
@@ -66,8 +68,9 @@ BODE_HD Layout make_layout(int n, int d, int S) {
 // aux sub-offsets (doubles)
 BODE_HD int aux_ck() { return kConsts; }
 BODE_HD int aux_ell() { return kConsts + kCkPad; }
-BODE_HD int aux_w() { return kConsts + 2 * kCkPad; }
-BODE_HD int aux_u(const Layout& L) { return kConsts + 2 * kCkPad + L.npad; }
+BODE_HD int aux_tab() { return kConsts + 2 * kCkPad; }
+BODE_HD int aux_w() { return kConsts + 2 * kCkPad + kTabPad; }
+BODE_HD int aux_u(const Layout& L) { return kConsts + 2 * kCkPad + kTabPad + L.npad; }
 
 // offset (doubles) of k4-group g inside a sample's tiled M; block (R, g), R >= g/2, sits at m_goff(g) + (R - g/2)*32
 BODE_HD size_t m_goff(int nrt, int g) {

@@ -22,6 +22,7 @@
 
 #include "layout.h"
 #include "prepare_args.h"
+#include "rbf.h"
 
 namespace bode {
 
@@ -103,7 +104,8 @@ __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
   double* Ld = Ljp + (size_t)npad * kNB;   // [8][8] diagonal block
   double* red = Ld + kNB * kNB;            // [8] reduction scratch
   double* ck = red + 8;                    // [16]
-  double* vec = ck + kCkPad;               // [npad] back-substitution right-hand side
+  double* tab = ck + kCkPad;               // [32] variance * 2^(j/32)
+  double* vec = tab + kTabPad;             // [npad] back-substitution right-hand side
   __shared__ int fail;
 
   double* aux = reinterpret_cast<double*>(a.ws + a.L.off_aux) + (size_t)s * a.L.aux_doubles;
@@ -118,12 +120,19 @@ __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
   const double noise = (a.ndim == d + 2) ? h[d + 1] * h[d + 1] : a.nugget_var;
   const double SQRT2 = 1.4142135623730951, SQRTPI = 1.7724538509055159;
   if (tid < kCkPad) ck[tid] = (tid < d) ? 1.0 / (SQRT2 * h[1 + tid]) : 0.0;
-  if (tid == 0) fail = 0;
+  if (tid >= 32 && tid < 32 + kTabPad) tab[tid - 32] = ss * exp2((double)(tid - 32) / 32.0);
+  if (tid == 0) {
+    // hyper-parameter sanity: the scoring kernel's exponent arithmetic assumes a sane variance scale
+    int bad = !(ss > 9.5e-7 && ss < 1.0e6) || !(noise >= 0.0 && noise < 1.0e6);
+    for (int k = 0; k < d; k++) bad |= !(h[1 + k] > 1e-300 && h[1 + k] < 1e300);
+    fail = bad ? -1 : 0;
+  }
   __syncthreads();
   if (tid < kCkPad) {
     aux[aux_ck() + tid] = ck[tid];
     aux[aux_ell() + tid] = (tid < d) ? h[1 + tid] : 1.0;
   }
+  if (tid >= 32 && tid < 32 + kTabPad) aux[aux_tab() + tid - 32] = tab[tid - 32];
 
   // ---- prescaled coordinates U, bordered rows e = xik(X) (row n) and Y (row n+1) ----------------------------
   for (int idx = tid; idx < npad * dpad; idx += kPrepThreads) {
@@ -161,7 +170,7 @@ __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
       const double t = ui[k] - uj[k];
       r2 = fma(t, t, r2);
     }
-    Lw[(size_t)i * npad + j] = ss * exp(-r2);
+    Lw[(size_t)i * npad + j] = rbf_exp(-r2, tab);
   }
   for (int idx = tid; idx < n * npad; idx += kPrepThreads) {
     const int i = idx / npad, j = idx - i * npad;
@@ -172,8 +181,8 @@ __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
 
   // ---- phase 1: bordered left-looking Cholesky -----------------------------------------------------------------
   const int nrows = n + 2;
-  int info = 0;
-  for (int j0 = 0; j0 < n; j0 += kNB) {
+  int info = fail;  // -1: rejected hyper-parameters
+  for (int j0 = 0; j0 < n && info == 0; j0 += kNB) {
     const int nb = min(kNB, n - j0);
     // stage panel rows j0..j0+7, columns [0, j0), as [k][8]
     for (int idx = tid; idx < j0 * kNB; idx += kPrepThreads) {
@@ -355,7 +364,7 @@ __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
 }
 
 size_t prepare_smem_bytes(const Layout& L) {
-  return sizeof(double) * ((size_t)L.npad * kNB + kNB * kNB + 8 + kCkPad + L.npad);
+  return sizeof(double) * ((size_t)L.npad * kNB + kNB * kNB + 8 + kCkPad + kTabPad + L.npad);
 }
 
 cudaError_t launch_prepare(const PrepArgs& a, cudaStream_t st) {

@@ -20,6 +20,7 @@
 #include <stdint.h>
 
 #include "layout.h"
+#include "rbf.h"
 #include "score_args.h"
 
 namespace bode {
@@ -29,16 +30,16 @@ namespace bode {
 // ----------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n"
@@ -47,18 +48,17 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(bar), "r"(parity)
       : "memory");
   return ok;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
-__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -100,14 +100,14 @@ __device__ __forceinline__ void phase_a(const double* __restrict__ aux, int aux_
                                         double* __restrict__ pv, double* __restrict__ xip, int tid) {
   constexpr int NJQ = kComputeThreads / C;
   const int c = tid % C, jq = tid / C;
-  const double ss = aux[C_SS];
   const double* ck = aux + aux_ck();
   const double* ell = aux + aux_ell();
+  const double* tab = aux + aux_tab();
   const double* w = aux + aux_w();
   const double* U = aux + aux_u_off;
   double y[DP];
 #pragma unroll
-  for (int k = 0; k < DP; k++) y[k] = xt[c * kXtStride + k] * ck[k];
+  for (int k = 0; k < DP; k++) y[k] = xt[k * C + c] * ck[k];
   double wk = 0.0;
   int g = jq;
   // two k4 groups (8 independent exp chains) per iteration
@@ -120,7 +120,7 @@ __device__ __forceinline__ void phase_a(const double* __restrict__ aux, int aux_
     }
     double kv[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) kv[i] = ss * exp(-r2[i]);
+    for (int i = 0; i < 8; i++) kv[i] = rbf_exp(-r2[i], tab);
     const double2 wa = *reinterpret_cast<const double2*>(w + 4 * g);
     const double2 wb = *reinterpret_cast<const double2*>(w + 4 * g + 2);
     const double2 wc = *reinterpret_cast<const double2*>(w + 4 * (g + NJQ));
@@ -137,7 +137,7 @@ __device__ __forceinline__ void phase_a(const double* __restrict__ aux, int aux_
   if (g < ng) {
     double kv[4];
 #pragma unroll
-    for (int kk = 0; kk < 4; kk++) kv[kk] = ss * exp(-sqdist<DP>(U + (size_t)(4 * g + kk) * dpad, y));
+    for (int kk = 0; kk < 4; kk++) kv[kk] = rbf_exp(-sqdist<DP>(U + (size_t)(4 * g + kk) * dpad, y), tab);
     const double2 wa = *reinterpret_cast<const double2*>(w + 4 * g);
     const double2 wb = *reinterpret_cast<const double2*>(w + 4 * g + 2);
     wk = fma(wa.x, kv[0], wk); wk = fma(wa.y, kv[1], wk); wk = fma(wb.x, kv[2], wk); wk = fma(wb.y, kv[3], wk);
@@ -149,7 +149,7 @@ __device__ __forceinline__ void phase_a(const double* __restrict__ aux, int aux_
   // xik factors of the dimensions k == jq (mod NJQ): sqrt(pi)/sqrt(2) * ell_k * (erf((1-x) ck) - erf((0-x) ck))
   double xf = 1.0;
   for (int k = jq; k < d; k += NJQ) {
-    const double x = xt[c * kXtStride + k];
+    const double x = xt[k * C + c];
     xf *= 1.2533141373155001 * ell[k] * (erf((1.0 - x) * ck[k]) - erf((0.0 - x) * ck[k]));
   }
   xip[jq * C + c] = xf;
@@ -176,38 +176,39 @@ __device__ __forceinline__ void phase_a_dispatch(const double* aux, int aux_u_of
 // All fragment loads of a group are issued before its DMMAs (no predicates, no per-slot branches).
 // ----------------------------------------------------------------------------------------------------------------
 template <int RT, int CT, int T0>
-__device__ __forceinline__ void run_groups(double (&acc)[RT][CT][2], const int (&tiles)[RT], const double* __restrict__ kc_lane,
-                                           const double* __restrict__ chunk_lane, size_t chunk_off0, int g, int g_end,
-                                           int C, int nrt) {
-#pragma unroll 2
+__device__ __forceinline__ void run_groups(double (&acc)[RT][CT][2], const int (&toff)[RT], const double* __restrict__ kc_lane,
+                                           const double* __restrict__ mb, int g, int g_end, int C, int nrt) {
+  // mb points at block (row tile g/2, group g) of the staged chunk (+lane); toff[t] = 32 * tile index of slot t
+  const double* kb = kc_lane + (size_t)g * C * 4;
   for (; g < g_end; ++g) {
     const int r0 = g >> 1;
-    const double* mb = chunk_lane + (m_goff(nrt, g) - chunk_off0);
-    const double* kb = kc_lane + (size_t)g * C * 4;
+    const double* m0 = mb - r0 * 32;
     double b[CT], a[RT - T0];
 #pragma unroll
     for (int ct = 0; ct < CT; ct++) b[ct] = kb[ct * 32];
 #pragma unroll
-    for (int t = T0; t < RT; t++) a[t - T0] = mb[(tiles[t] - r0) * 32];
+    for (int t = T0; t < RT; t++) a[t - T0] = m0[toff[t]];
 #pragma unroll
     for (int t = T0; t < RT; t++)
 #pragma unroll
       for (int ct = 0; ct < CT; ct++) dmma884(acc[t][ct][0], acc[t][ct][1], a[t - T0], b[ct]);
+    mb += (nrt - r0) * 32;
+    kb += C * 4;
   }
 }
 
 template <int RT, int CT, int T0 = 0>
 struct SegDispatch {
-  static __device__ __forceinline__ void run(int t0, double (&acc)[RT][CT][2], const int (&tiles)[RT], const double* kc_lane,
-                                             const double* chunk_lane, size_t chunk_off0, int g, int g_end, int C, int nrt) {
-    if (t0 == T0) run_groups<RT, CT, T0>(acc, tiles, kc_lane, chunk_lane, chunk_off0, g, g_end, C, nrt);
-    else SegDispatch<RT, CT, T0 + 1>::run(t0, acc, tiles, kc_lane, chunk_lane, chunk_off0, g, g_end, C, nrt);
+  static __device__ __forceinline__ void run(int t0, double (&acc)[RT][CT][2], const int (&toff)[RT], const double* kc_lane,
+                                             const double* mb, int g, int g_end, int C, int nrt) {
+    if (t0 == T0) run_groups<RT, CT, T0>(acc, toff, kc_lane, mb, g, g_end, C, nrt);
+    else SegDispatch<RT, CT, T0 + 1>::run(t0, acc, toff, kc_lane, mb, g, g_end, C, nrt);
   }
 };
 template <int RT, int CT>
 struct SegDispatch<RT, CT, RT> {
   static __device__ __forceinline__ void run(int, double (&)[RT][CT][2], const int (&)[RT], const double*, const double*,
-                                             size_t, int, int, int, int) {}
+                                             int, int, int, int) {}
 };
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -223,21 +224,25 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const Layout& L = a.L;
   const int nrt = L.nrt, ng = L.ng, npad = L.npad;
+  const int stages = a.stages, nchunks = a.nchunks;
 
   // ---- shared memory carve-up (offsets in doubles; everything 16-byte aligned) ----
   double* Kc = reinterpret_cast<double*>(smem_raw);             // [ng][C][4]
   double* auxs = Kc + (size_t)npad * C;                          // aux block of the current sample
   double* ring = auxs + L.aux_doubles;                           // [stages][chunk_max]
-  double* red = ring + (size_t)a.stages * a.chunk_max;           // [RG][C]
+  double* red = ring + (size_t)stages * a.chunk_max;             // [RG][C]
   double* pv = red + RG * C;                                     // [2][NJQ][C]   (NJQ*C = kComputeThreads)
   double* xip = pv + 2 * kComputeThreads;                        // [2][NJQ][C]
-  double* xt = xip + 2 * kComputeThreads;                        // [C][kXtStride]
+  double* xt = xip + 2 * kComputeThreads;                        // [kXtStride][C]  candidate tile, dimension-major
   uint64_t* bars = reinterpret_cast<uint64_t*>(xt + C * kXtStride);
-  uint64_t* full = bars;                  // [stages]
-  uint64_t* empty = bars + kMaxStages;    // [stages]
-  uint64_t* aux_full = bars + 2 * kMaxStages;
-  uint64_t* aux_empty = aux_full + 1;
-  int* seg_end = reinterpret_cast<int*>(aux_empty + 1);  // [RG][RT+1]: k4 group at which slot t dies
+  const uint32_t full0 = smem_u32(bars);                          // full[stages]
+  const uint32_t empty0 = full0 + 8 * kMaxStages;                 // empty[stages]
+  const uint32_t aux_full = empty0 + 8 * kMaxStages;
+  const uint32_t aux_empty = aux_full + 8;
+  // per-row-group phase-B program, built once per CTA: entries (g_begin | g_end<<10 | t0<<20 | first<<26 | last<<27)
+  const int prog_stride = nchunks + kMaxRT;
+  int* prog = reinterpret_cast<int*>(bars + 2 * kMaxStages + 2);  // [RG][prog_stride]
+  int* prog_len = prog + RG * prog_stride;                        // [RG]
 
   // ---- work item ----
   const int item = blockIdx.x;
@@ -246,21 +251,38 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
   const int64_t c0 = (int64_t)tile * C;
 
   if (tid == 0) {
-    for (int i = 0; i < a.stages; i++) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], kComputeWarps);
+    for (int i = 0; i < stages; i++) {
+      mbar_init(full0 + 8 * i, 1);
+      mbar_init(empty0 + 8 * i, kComputeWarps);
     }
     mbar_init(aux_full, 1);
     mbar_init(aux_empty, kComputeWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (tid < RG * (RT + 1)) {
-    const int r = tid / (RT + 1), t = tid - r * (RT + 1);
-    seg_end[tid] = (t < RT) ? 2 * (int)a.tile_id[r * kMaxRT + t] + 2 : 0x7fffffff;  // unused slot (-1) -> 0
+  if (tid < RG) {
+    // segments of constant live-slot count, cut at chunk boundaries; every chunk gets at least one entry so that
+    // every warp waits on / releases every ring stage exactly once per chunk.
+    const short* tl = a.tile_id + tid * kMaxRT;
+    int* pr = prog + tid * prog_stride;
+    int np = 0, t0 = 0;
+    for (int q = 0; q < nchunks; q++) {
+      int g = a.chunk_g0[q];
+      const int g_hi = a.chunk_g0[q + 1];
+      bool first = true;
+      while (g < g_hi) {
+        while (t0 < RT && 2 * (int)tl[t0] + 2 <= g) t0++;
+        const int ge = (t0 < RT) ? min(g_hi, 2 * (int)tl[t0] + 2) : g_hi;
+        const bool last = (ge == g_hi);
+        pr[np++] = g | (ge << 10) | (t0 << 20) | ((first ? 1 : 0) << 26) | ((last ? 1 : 0) << 27);
+        first = false;
+        g = ge;
+      }
+    }
+    prog_len[tid] = np;
   }
-  // candidate tile -> smem (rows beyond Nd are filled with a harmless interior point)
+  // candidate tile -> smem, dimension-major (rows beyond Nd are filled with a harmless interior point)
   for (int idx = tid; idx < C * kXtStride; idx += kScoreThreads) {
-    const int c = idx / kXtStride, k = idx - c * kXtStride;
+    const int k = idx / C, c = idx - k * C;
     double v = 0.5;
     if (k < L.d && c0 + c < a.Nd) v = a.Xd[(c0 + c) * L.d + k];
     xt[idx] = v;
@@ -275,23 +297,30 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
   if (warp >= kComputeWarps) {
     // ============================ producer warpgroup (one elected lane of its first warp) ========================
     // Register budget: the CTA launches with 20 warps x 96 registers; this warpgroup shrinks to 24 so that the four
-    // compute warpgroups can grow to 112 out of the registers it releases (setmaxnreg is warpgroup-collective, hence a full group of 4 warps here).
+    // compute warpgroups can grow to 112 out of the registers it releases (setmaxnreg is warpgroup-collective and
+    // the pool is per CTA, hence a full group of 4 warps here).
     asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
     if (warp == kComputeWarps && lane == 0) {
-      uint32_t it = 0;  // running chunk counter -> ring stage / parity
+      const uint32_t ring_u32 = smem_u32(ring), auxs_u32 = smem_u32(auxs);
+      const uint32_t chunk_bytes_max = (uint32_t)a.chunk_max * 8u;
+      int st = 0;
+      uint32_t ph = 0;  // parity of the ring round currently being filled
+      bool first_round = true;
       for (int s = s_begin; s < s_end; s++) {
         const int ls = s - s_begin;
         if (ls > 0) mbar_wait(aux_empty, (uint32_t)((ls - 1) & 1));
         mbar_arrive_expect_tx(aux_full, aux_bytes);
-        bulk_copy_g2s(auxs, aux_g + (size_t)s * L.aux_doubles, aux_bytes, aux_full);
+        bulk_copy_g2s(auxs_u32, aux_g + (size_t)s * L.aux_doubles, aux_bytes, aux_full);
         const double* ms = m_g + (size_t)s * L.m_doubles;
-        for (int q = 0; q < a.nchunks; q++, it++) {
-          const uint32_t st = it % (uint32_t)a.stages, round = it / (uint32_t)a.stages;
-          if (round > 0) mbar_wait(&empty[st], (round - 1) & 1);
-          const size_t o0 = m_goff(nrt, a.chunk_g0[q]), o1 = m_goff(nrt, a.chunk_g0[q + 1]);
+        size_t o0 = 0;
+        for (int q = 0; q < nchunks; q++) {
+          if (!first_round) mbar_wait(empty0 + 8 * st, ph ^ 1);
+          const size_t o1 = m_goff(nrt, a.chunk_g0[q + 1]);
           const uint32_t bytes = (uint32_t)((o1 - o0) * sizeof(double));
-          mbar_arrive_expect_tx(&full[st], bytes);
-          bulk_copy_g2s(ring + (size_t)st * a.chunk_max, ms + o0, bytes, &full[st]);
+          mbar_arrive_expect_tx(full0 + 8 * st, bytes);
+          bulk_copy_g2s(ring_u32 + (uint32_t)st * chunk_bytes_max, ms + o0, bytes, full0 + 8 * st);
+          o0 = o1;
+          if (++st == stages) { st = 0; ph ^= 1; first_round = false; }
         }
       }
     }
@@ -302,14 +331,17 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
   asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
   const int rg = warp % RG, cg = warp / RG;
   const int cbase = cg * CT * 8;
-  int tiles[RT];
+  int toff[RT];
 #pragma unroll
-  for (int t = 0; t < RT; t++) tiles[t] = a.tile_id[rg * kMaxRT + t];
-  const int* my_seg_end = seg_end + rg * (RT + 1);
+  for (int t = 0; t < RT; t++) toff[t] = 32 * (int)a.tile_id[rg * kMaxRT + t];
+  const int* my_prog = prog + rg * prog_stride;
+  const int my_len = prog_len[rg];
   const double* kc_lane = Kc + (size_t)cbase * 4 + lane;
+  const double* ring_lane = ring + lane;
 
   const int aux_u_off = aux_u(L);
-  uint32_t it = 0;
+  int st = 0;
+  uint32_t ph = 0;
   for (int s = s_begin; s < s_end; s++) {
     const int ls = s - s_begin, par = ls & 1;
     double* pvp = pv + par * kComputeThreads;
@@ -330,23 +362,27 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
 #pragma unroll
       for (int ct = 0; ct < CT; ct++) { acc[t][ct][0] = 0.0; acc[t][ct][1] = 0.0; }
 
-    int g = 0, t0 = 0;
-    for (int q = 0; q < a.nchunks; q++, it++) {
-      const uint32_t st = it % (uint32_t)a.stages, round = it / (uint32_t)a.stages;
-      mbar_wait(&full[st], round & 1);
-      const double* chunk_lane = ring + (size_t)st * a.chunk_max + lane;
-      const int g_hi = a.chunk_g0[q + 1];
-      const size_t chunk_off0 = m_goff(nrt, a.chunk_g0[q]);
-      while (g < g_hi) {
-        while (my_seg_end[t0] <= g) t0++;   // sentinel at [RT] stops the scan
-        if (t0 >= RT) { g = g_hi; break; }
-        const int ge = min(g_hi, my_seg_end[t0]);
-        SegDispatch<RT, CT>::run(t0, acc, tiles, kc_lane, chunk_lane, chunk_off0, g, ge, C, nrt);
-        g = ge;
+    const double* mb = ring_lane;
+    for (int i = 0; i < my_len; i++) {
+      const int e = my_prog[i];
+      const int g = e & 1023, ge = (e >> 10) & 1023, t0 = (e >> 20) & 63;
+      if (e & (1 << 26)) {
+        mbar_wait(full0 + 8 * st, ph);
+        mb = ring_lane + (size_t)st * a.chunk_max;
       }
-      g = g_hi;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[st]);
+      SegDispatch<RT, CT>::run(t0, acc, toff, kc_lane, mb, g, ge, C, nrt);
+      // advance mb over the groups [g, ge) of this chunk: sum_{g'} (nrt - g'/2) blocks
+      {
+        const int a0 = g >> 1, a1 = ge >> 1;  // closed form of sum_{g'=g}^{ge-1} (nrt - (g' >> 1))
+        const int full_pairs = 2 * ((a1 - a0) * nrt - (a1 * (a1 - 1) - a0 * (a0 - 1)) / 2);
+        const int adj = ((ge & 1) ? (nrt - a1) : 0) - ((g & 1) ? (nrt - a0) : 0);
+        mb += (full_pairs + adj) * 32;
+      }
+      if (e & (1 << 27)) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8 * st);
+        if (++st == stages) { st = 0; ph ^= 1; }
+      }
     }
 
     // ---- column sums of squares over this warp's rows -> red[rg][c] ----
@@ -488,10 +524,10 @@ __global__ void k_exp_inplace(double* __restrict__ v, size_t n) {
 // ----------------------------------------------------------------------------------------------------------------
 // Host-side planning and launch
 // ----------------------------------------------------------------------------------------------------------------
-static size_t score_smem_bytes(const Layout& L, int C, int RG, int stages, int chunk_max) {
+static size_t score_smem_bytes(const Layout& L, int C, int RG, int stages, int chunk_max, int nchunks) {
   size_t dbl = (size_t)L.npad * C + L.aux_doubles + (size_t)stages * chunk_max + (size_t)RG * C + 4 * kComputeThreads +
                (size_t)C * kXtStride;
-  return dbl * sizeof(double) + sizeof(uint64_t) * (2 * kMaxStages + 2) + sizeof(int) * kMaxRG * (kMaxRT + 1) + 128;
+  return dbl * sizeof(double) + sizeof(uint64_t) * (2 * kMaxStages + 2) + sizeof(int) * ((size_t)RG * (nchunks + kMaxRT) + kMaxRG + 8) + 128;
 }
 
 // Longest-processing-time assignment of row tiles (weight R+1 ~ number of live k4 groups) to the row groups.
@@ -544,11 +580,11 @@ int plan_score(const Layout& L, int64_t Nd, int sm_count, size_t smem_optin, Sco
   P->nchunks = nch;
   P->chunk_max = (int)chunk_max;
   int stages = kMaxStages;
-  while (stages >= 2 && score_smem_bytes(L, C, P->rg, stages, (int)chunk_max) > smem_optin) stages--;
+  while (stages >= 2 && score_smem_bytes(L, C, P->rg, stages, (int)chunk_max, nch) > smem_optin) stages--;
   if (stages < 2) return -1;
   if (stages > nch + 1 && nch + 1 >= 2) stages = nch + 1;
   P->stages = stages;
-  P->smem = score_smem_bytes(L, C, P->rg, stages, (int)chunk_max);
+  P->smem = score_smem_bytes(L, C, P->rg, stages, (int)chunk_max, nch);
   assign_tiles(nrt, P->rg, P->rt, P->tile_id);
   // work items: (tile, sample chunk); aim for >= 16 waves of CTAs, keep at least 4 samples per item when possible
   const int64_t ntiles = (Nd + C - 1) / C;

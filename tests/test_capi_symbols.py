@@ -1,0 +1,67 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/bode_b200.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "bode_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(bode_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_declares_the_expected_entry_points():
+    syms = header_symbols()
+    for s in ("bode_ekld_prepare_dev", "bode_ekld_score_dev", "bode_ekld_score_host", "bode_ekld_mu_sigma_dev",
+              "bode_us_variance_dev", "bode_gp_loglik_host", "bode_ekld_workspace_bytes", "bode_fp64_peak"):
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    lib = ctypes.CDLL(built_lib)
+    for s in header_symbols():
+        assert hasattr(lib, s), "missing export %s" % s
+    from bode_b200 import _ext
+    assert set(_ext.EXPORTS) == set(header_symbols())
+
+
+def test_pure_host_entry_points(built_lib):
+    from bode_b200 import _ext
+    lib = _ext.load()
+    assert lib.bode_version().decode().startswith("bode_b200")
+    assert lib.bode_strerror(0) == b"ok" and b"unsupported" in lib.bode_strerror(-2)
+    # workspace sizing: monotone in S, zero for unsupported shapes
+    w1 = lib.bode_ekld_workspace_bytes(200, 8, 64)
+    w2 = lib.bode_ekld_workspace_bytes(200, 8, 128)
+    assert 0 < w1 < w2 and w1 % 256 == 0
+    assert lib.bode_ekld_workspace_bytes(2000, 8, 4) == 0
+    assert lib.bode_ekld_workspace_bytes(10, 17, 4) == 0
+    assert lib.bode_ekld_score_scratch_bytes(100000) >= (100000 // 256) * 16
+    # argument validation happens before any CUDA call
+    z = np.zeros(4)
+    p = ctypes.c_void_p(z.ctypes.data)
+    assert lib.bode_ekld_prepare_dev(None, p, p, 2, 1, 1, 2, 1e-6, 1e-8, p, 0, p, None) == -1
+    assert lib.bode_ekld_prepare_dev(p, p, p, 2, 1, 1, 5, 1e-6, 1e-8, p, 0, p, None) == -1
+    assert lib.bode_ekld_prepare_dev(p, p, p, 2000, 1, 1, 2, 1e-6, 1e-8, p, 0, p, None) == -2
+    assert lib.bode_ekld_prepare_dev(p, p, p, 2, 1, 1, 2, 1e-6, 1e-8, p, 16, p, None) == -3
+
+
+def test_no_cpu_fallback_without_gpu(built_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from bode_b200 import _ext
+    from bode_b200.engine import EkldEngine
+    with pytest.raises(RuntimeError):
+        EkldEngine()
+    with pytest.raises(_ext.BodeError) as ei:
+        _ext.ekld_score_host(np.random.rand(5, 2), np.random.rand(5), np.random.rand(3, 3) + 0.1, np.random.rand(7, 2), 1e-6)
+    assert ei.value.status == -4
+    import bode_b200
+    with pytest.raises(RuntimeError):
+        bode_b200.KLSampler(np.random.rand(3, 1), np.random.rand(3, 1), False, lambda x: 0.0, False, [(0, 1)], mcmc_model=True)

@@ -1,0 +1,283 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle, the golden fixture and the long-double
+arbiter.  Tolerance model: tests/tolerance.py.  Nothing here reads /root/reference."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ekld_oracle as orc
+from oracle import truth
+from tests import cases
+from tests.tolerance import assert_argmax, assert_parity, assert_score, assert_t1, assert_t2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ext(built_lib):
+    from bode_b200 import _ext
+    _ext.load()
+    return _ext
+
+
+@pytest.fixture(scope="module")
+def engine(built_lib):
+    from bode_b200.engine import EkldEngine
+    return EkldEngine()
+
+
+def gpu_score(ext, X, Y, hyp, Xd, nugget=1e-3, **kw):
+    return ext.ekld_score_host(X, Y, hyp, Xd, nugget ** 2, want_kld=True, **kw)
+
+
+# ---- golden fixture ---------------------------------------------------------------------------------------------
+def test_fixture_known_answer_on_gpu(ext, golden_dir):
+    """comp.pkl (reference tests/mcmc_ex1_n=3_it=1): mean_s mu_1 and mean_s sigma_1 from the prepare kernel."""
+    comp = np.load(os.path.join(golden_dir, "comp_ex1.npz"))
+    X, Y = cases.ex1_problem()
+    r = gpu_score(ext, X, Y, comp["models_it0"], np.array([[0.5]]))
+    assert abs(r["mu_Q"] - comp["mu_us"][0]) <= 1e-12 * abs(comp["mu_us"][0])
+    assert abs(r["sigma_Q"] - comp["sigma_us"][0]) <= 1e-9 * abs(comp["sigma_us"][0])
+
+
+def test_config1_samp_ex1_dense(ext, golden_dir):
+    """BASELINE config 1: d=1, n=3, S=60 fixture hyper-samples, 1000 centred-LHS candidates.  Several fixture
+    samples are ill-conditioned (variance 14, ell 1.4 on 3 points), hence the T2 model."""
+    comp = np.load(os.path.join(golden_dir, "comp_ex1.npz"))
+    X, Y = cases.ex1_problem()
+    Xd = ((np.arange(1000) + 0.5) / 1000)[:, None]
+    r = gpu_score(ext, X, Y, comp["models_it0"], Xd)
+    ref = orc.score(X, Y, Xd, comp["models_it0"])
+    t = truth.ekld_truth(X, Y, Xd, comp["models_it0"])
+    assert_t2(r["kld"], ref["kld"], t["kld"])
+    # the design is mirror-symmetric, so indices 0 and 999 tie up to rounding: tie-set argmax rule
+    assert_argmax(r["argmax"], np.log(t["kld"]).mean(0), tol=1e-6)
+    assert r["argmax"] == int(np.argmax(r["score"]))
+    assert (r["info"] == 0).all() and not np.isnan(r["score"]).any()
+
+
+# ---- T1: well-conditioned families, element-wise 1e-9 -------------------------------------------------------------
+@pytest.mark.parametrize("d,n,S,Nd,lo,hi", [
+    (3, 24, 6, 500, 0.08, 0.25),
+    (6, 60, 16, 2000, 0.15, 0.5),
+    (8, 120, 8, 1500, 0.15, 0.9),
+    (8, 200, 8, 1000, 0.2, 0.9),      # config-3 shape (n=200 -> 25 row tiles, variant 0)
+    (5, 8, 4, 300, 0.3, 0.9),         # exactly one row tile
+    (5, 9, 4, 300, 0.3, 0.9),         # one row tile + 1 row
+    (4, 1, 3, 100, 0.3, 0.9),         # a single observation
+    (12, 40, 4, 200, 0.3, 0.9),
+    (16, 33, 3, 100, 0.4, 0.9),       # maximum supported dimension
+])
+def test_t1_elementwise(ext, d, n, S, Nd, lo, hi):
+    X, Y, Xd, hyp = cases.make_problem(d, n, S, Nd, seed=1000 + 7 * d + n, ell_lo=lo, ell_hi=hi)
+    r = gpu_score(ext, X, Y, hyp, Xd)
+    ref = orc.score(X, Y, Xd, hyp)
+    t = truth.ekld_truth(X, Y, Xd, hyp)
+    assert (r["info"] == 0).all()
+    trusted = assert_parity(r["kld"], ref["kld"], t["kld"], min_trusted=0.75)
+    if trusted.all():
+        assert_score(r["score"], ref["score"], ref["kld"])
+        np.testing.assert_allclose(r["var"], ref["var"], rtol=1e-6, atol=1e-9)
+    assert_argmax(r["argmax"], ref["score"])
+    assert abs(r["mu_Q"] - ref["mu_Q"]) <= 1e-10 * abs(ref["mu_Q"]) + 1e-13
+    assert abs(r["sigma_Q"] - ref["sigma_Q"]) <= 1e-8 * abs(ref["sigma_Q"])
+
+
+@pytest.mark.parametrize("n,variant_note", [(257, "RT16/CT1, 4x4 warps"), (500, "config-4 shape"), (513, "8x2 warps"), (700, "8x2 warps")])
+def test_large_n_variants(ext, n, variant_note):
+    """n > 256 and n > 512 switch kernel template variants; same tolerance."""
+    d, S, Nd = 10, 3, 150
+    X, Y, Xd, hyp = cases.make_problem(d, n, S, Nd, seed=n, ell_lo=0.3, ell_hi=0.9)
+    r = gpu_score(ext, X, Y, hyp, Xd)
+    ref = orc.score(X, Y, Xd, hyp)
+    t = truth.ekld_truth(X, Y, Xd, hyp)
+    assert_t2(r["kld"], ref["kld"], t["kld"])
+    assert_argmax(r["argmax"], ref["score"])
+    np.testing.assert_allclose(r["mu_Q"], ref["mu_Q"], rtol=1e-9)
+
+
+def test_noisy_layout_d_plus_2(ext):
+    """noisy=True rows carry the noise std in the last column (`_sampler.py:454-457`)."""
+    X, Y, Xd, hyp = cases.make_problem(4, 30, 5, 400, seed=3, ell_lo=0.15, ell_hi=0.5, noisy=True)
+    r = gpu_score(ext, X, Y, hyp, Xd)
+    ref = orc.score(X, Y, Xd, hyp)
+    t = truth.ekld_truth(X, Y, Xd, hyp)
+    assert_parity(r["kld"], ref["kld"], t["kld"], min_trusted=0.5)
+    assert_argmax(r["argmax"], ref["score"])
+
+
+# ---- T2: prior-drawn (ill-conditioned) hyper-samples, arbitration against the 80-bit truth --------------------------
+@pytest.mark.parametrize("d,n,S,Nd,seed", [(2, 30, 32, 1000, 1263), (1, 8, 24, 300, 4), (6, 60, 24, 300, 1), (8, 200, 16, 300, 1223)])
+def test_t2_prior_draws(ext, d, n, S, Nd, seed):
+    X, Y, Xd, hyp = cases.prior_problem(d, n, S, Nd, seed)
+    r = gpu_score(ext, X, Y, hyp, Xd, raise_not_pd=False)
+    ok = r["info"] == 0
+    assert ok.all()
+    ref = orc.score(X, Y, Xd, hyp)
+    t = truth.ekld_truth(X, Y, Xd, hyp)
+    eg, eo = assert_t2(r["kld"], ref["kld"], t["kld"])
+    assert eg.max() <= 1e-6  # the triangular route stays accurate where dpotri does not (SURVEY note C)
+    assert_argmax(r["argmax"], np.log(t["kld"]).mean(0), tol=1e-6)
+
+
+def test_log1p_form_tracks_truth(ext):
+    """BODE_FORM_LOG1P removes the reference expression's 2e-16 absolute noise: tiny EKLDs keep full precision."""
+    X, Y, Xd, hyp = cases.make_problem(6, 60, 8, 500, seed=21, ell_lo=0.1, ell_hi=0.3)
+    r = ext.ekld_score_host(X, Y, hyp, Xd, 1e-6, form=ext.BODE_FORM_LOG1P, want_kld=True)
+    t = truth.ekld_truth(X, Y, Xd, hyp)
+    np.testing.assert_allclose(r["kld"], t["kld"], rtol=1e-9, atol=0)
+
+
+# ---- shapes and edge cases ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("Nd", [1, 2, 63, 64, 65, 127, 1000])
+def test_ragged_candidate_counts(ext, Nd):
+    X, Y, Xd, hyp = cases.make_problem(3, 20, 5, 1000, seed=9, ell_lo=0.2, ell_hi=0.7)
+    full = gpu_score(ext, X, Y, hyp, Xd)
+    part = gpu_score(ext, X, Y, hyp, Xd[:Nd])
+    np.testing.assert_array_equal(part["score"], full["score"][:Nd])  # bit-identical regardless of tiling
+    np.testing.assert_array_equal(part["kld"], full["kld"][:, :Nd])
+    assert part["argmax"] == int(np.argmax(part["score"]))
+
+
+def test_sharding_and_permutation_invariance_bitwise(engine):
+    """A candidate's score does not depend on its position, tile or shard: the multi-GPU determinism guarantee."""
+    X, Y, Xd, hyp = cases.make_problem(8, 200, 16, 5000, seed=77, ell_lo=0.2, ell_hi=0.9)
+    engine.prepare(X, Y, hyp, 1e-6)
+    full = engine.score(Xd)["score"].cpu().numpy()
+    perm = np.random.default_rng(0).permutation(Xd.shape[0])
+    np.testing.assert_array_equal(engine.score(Xd[perm])["score"].cpu().numpy(), full[perm])
+    from bode_b200.dist import shard_bounds
+    for world in (2, 4, 8):
+        parts, bests = [], []
+        for r in range(world):
+            lo, hi = shard_bounds(Xd.shape[0], world, r)
+            res = engine.score(Xd[lo:hi], idx_offset=lo)
+            parts.append(res["score"].cpu().numpy()); bests.append((float(res["best"].item()), int(res["best_idx"].item())))
+        np.testing.assert_array_equal(np.concatenate(parts), full)
+        assert max(bests, key=lambda b: (b[0], -b[1]))[1] == int(np.argmax(full))
+
+
+def test_single_candidate_wrapper_mcmc_kld(engine):
+    """KLSampler.mcmc_kld(x) == column of the dense result, and == the literal per-candidate oracle."""
+    import bode_b200
+    X, Y, Xd, hyp = cases.make_problem(3, 15, 6, 40, seed=13, ell_lo=0.2, ell_hi=0.7)
+    kls = bode_b200.KLSampler(X, Y, False, lambda x: 0.0, False, [(0, 1)] * 3, mcmc_model=True, mcmc_chains=2, mcmc_model_avg=6,
+                              mcmc_steps=40, mcmc_burn=10, mcmc_thin=5, engine=engine, hyper_samples=lambda X_, Y_, it: hyp)
+    for c in (0, 7, 39):
+        m, v = kls.mcmc_kld(Xd[c], kls.model)
+        mo, vo = orc.mcmc_kld_literal(Xd[c], X, Y, hyp, nugget=1e-3)
+        assert abs(m - mo) <= 1e-9 and abs(v - vo) <= 1e-7 * abs(vo) + 1e-12
+
+
+def test_not_positive_definite_is_reported(ext):
+    """Duplicate observations with zero nugget and zero jitter: LAPACK-style info > 0, NaN score, NaN wins argmax."""
+    rng = np.random.default_rng(0)
+    X = rng.random((6, 2)); X[4] = X[1]
+    Y = rng.random((6, 1))
+    hyp = np.array([[1.0, 0.5, 0.5], [2.0, 0.4, 0.6]])
+    with pytest.raises(ext.BodeError) as ei:
+        ext.ekld_score_host(X, Y, hyp, rng.random((10, 2)), 0.0, jitter=0.0)
+    assert ei.value.status == -5
+    r = ext.ekld_score_host(X, Y, hyp, rng.random((10, 2)), 0.0, jitter=0.0, raise_not_pd=False)
+    assert (r["info"] > 0).all() and np.isnan(r["score"]).all() and r["argmax"] == 0
+
+
+def test_invalid_hyperparameters_are_rejected(ext):
+    X, Y, Xd, hyp = cases.make_problem(2, 10, 3, 20, seed=2)
+    hyp[1, 1] = -0.3   # negative lengthscale
+    hyp[2, 0] = np.nan
+    r = ext.ekld_score_host(X, Y, hyp, Xd, 1e-6, raise_not_pd=False)
+    assert r["info"].tolist() == [0, -1, -1]
+
+
+def test_unsupported_shapes_fail_loudly(ext):
+    with pytest.raises(ext.BodeError) as ei:
+        ext.ekld_score_host(np.random.rand(1100, 2), np.random.rand(1100), np.ones((2, 3)), np.random.rand(4, 2), 1e-6)
+    assert ei.value.status == -2
+    with pytest.raises(ext.BodeError) as ei:
+        ext.ekld_score_host(np.random.rand(10, 2), np.random.rand(10), np.ones((2, 5)), np.random.rand(4, 2), 1e-6)
+    assert ei.value.status == -1
+
+
+# ---- next-row components that reuse the kernels -----------------------------------------------------------------------
+def test_us_variance_comparator(engine):
+    """update_comp_models (`_sampler.py:506-514`): argmax of mean_s latent predictive variance."""
+    X, Y, Xg, hyp = cases.make_problem(3, 25, 10, 1000, seed=31, ell_lo=0.2, ell_hi=0.7)
+    engine.prepare(X, Y, hyp, 1e-6)
+    r = engine.us_variance(Xg)
+    pv, j = orc.us_variance(X, Y, Xg, hyp)
+    np.testing.assert_allclose(r["pred_var"].cpu().numpy(), pv, rtol=1e-8, atol=1e-13)
+    assert int(r["best_idx"].item()) == j
+
+
+def test_batched_log_likelihood(ext):
+    """GPy log_marginal for the host MCMC (`_sampler.py:221-232`), one launch for a whole half-ensemble."""
+    X, Y, _, hyp = cases.make_problem(5, 50, 12, 4, seed=41, ell_lo=0.2, ell_hi=0.9)
+    ll = ext.gp_loglik_host(X, Y, hyp, 1e-6)
+    np.testing.assert_allclose(ll, orc.log_likelihoods(X, Y, hyp), rtol=1e-10)
+
+
+# ---- full-size properties (BASELINE config 3: d=8, n=200, S=64, |X_design|=1e5) ----------------------------------------
+def test_config3_full_size_properties(engine):
+    rng = np.random.default_rng(1223)
+    n, d, S, Nd = 200, 8, 64, 100000
+    X = rng.random((n, d))
+    Y = cases.dette8(X)[:, None]
+    Xd = rng.random((Nd, d))
+    hyp = np.column_stack([rng.gamma(2.0, 1.0, S) + 0.2] + [rng.uniform(0.2, 0.9, S) for _ in range(d)])
+    engine.prepare(X, Y, hyp, 1e-6)
+    res = engine.score(Xd)
+    score = res["score"].cpu().numpy()
+    assert int(engine.info.max()) == 0 and not np.isnan(score).any()
+    assert int(res["best_idx"].item()) == int(np.argmax(score)) and float(res["best"].item()) == score.max()
+    # EKLD >= 0 up to the reference expression's 2e-16 absolute noise: exp(logk) finite and positive
+    logk = res["logk"]
+    assert bool((logk == logk).all())
+    # parity on a seeded random subset the oracle finishes in seconds
+    sub = rng.choice(Nd, size=600, replace=False)
+    ref = orc.score(X, Y, Xd[sub], hyp)
+    t = truth.ekld_truth(X, Y, Xd[sub], hyp)
+    got_kld = np.exp(logk[:, sub].cpu().numpy())
+    trusted = assert_parity(got_kld, ref["kld"], t["kld"], min_trusted=0.5)
+    tsc = np.log(t["kld"]).mean(0)
+    # vs the long-double truth over all 64 samples (trusted or not): 1e-8 relative per entry plus the reference
+    # expression's 1e-15 absolute noise, propagated through log and the mean over hyper-samples
+    assert (np.abs(score[sub] - tsc) <= 2.0 * np.mean(1e-8 + 1e-15 / t["kld"], axis=0)).all()
+    # the winner is also the oracle's winner among {winner} + subset
+    j = int(res["best_idx"].item())
+    tj = np.log(truth.ekld_truth(X, Y, Xd[[j]], hyp)["kld"]).mean(0)[0]
+    assert tj >= tsc.max() - 1e-7
+
+
+def test_sequential_loop_matches_oracle_loop(engine):
+    """BASELINE config 5 (reduced): full KLSampler.optimize loop on a 6-D function with the host MCMC replaced by a
+    shared, seeded hyper-sample generator so the CPU oracle loop sees identical hyper-samples every iteration."""
+    import bode_b200
+    d, n0, S, Nd, iters = 6, 20, 12, 3000, 6
+    rng = np.random.default_rng(5)
+    X0 = rng.random((n0, d))
+    Y0 = np.array([cases.ex4_func6(x) for x in X0])[:, None]
+    Xd = rng.random((Nd, d))
+
+    def hyper(X, Y, it):
+        r = np.random.default_rng(1000 + it)
+        return np.column_stack([r.gamma(2.0, 1.0, S) + 0.2] + [r.uniform(0.25, 0.9, S) for _ in range(d)])
+
+    kls = bode_b200.KLSampler(X0, Y0, False, cases.ex4_func6, False, [(0, 1)] * d, mcmc_model=True, max_it=iters, kld_tol=0.0,
+                              mcmc_chains=2, mcmc_model_avg=S, mcmc_steps=100, mcmc_burn=10, mcmc_thin=5,
+                              X_design=Xd, engine=engine, hyper_samples=hyper)
+    Xg, Yg, _, kld_all, _, mu_qoi, sigma_qoi = kls.optimize(num_designs=Nd)
+    # oracle loop
+    X, Y = X0.copy(), Y0.copy()
+    chosen = []
+    for it in range(iters):
+        ref = orc.score(X, Y, Xd, hyper(X, Y, it))
+        chosen.append(ref["argmax"])
+        assert abs(mu_qoi[it] - ref["mu_Q"]) <= 1e-9 * abs(ref["mu_Q"]) + 1e-12
+        assert abs(sigma_qoi[it] - ref["sigma_Q"]) <= 1e-7 * abs(ref["sigma_Q"])
+        assert_score(np.log(kld_all[it]), ref["score"], ref["kld"])
+        x = Xd[ref["argmax"]]
+        X = np.vstack([X, x[None]]); Y = np.vstack([Y, [[cases.ex4_func6(x)]]])
+    assert kls.chosen_idx == chosen           # identical chosen design sequence
+    np.testing.assert_array_equal(Xg, X)
+    assert kld_all.shape == (iters, Nd) and len(mu_qoi) == iters + 1

@@ -1,0 +1,124 @@
+"""CPU: host-side pieces that surround the device path (designs, ensemble sampler, argmax combine, exports)."""
+import numpy as np
+import pytest
+import torch
+
+import bode_b200
+from bode_b200 import _emcee, _lhs, dist
+from bode_b200._core import JeffreysPrior, UniformPrior
+
+
+def test_package_exports_reference_names():
+    import bode
+    for name in ['xik', 'bk', 'JeffreysPrior', 'BetaPrior', 'GammaPrior', 'UniformPrior', 'ExponentialPrior', 'ei', 'KLSampler']:
+        assert name in bode_b200.__all__ and hasattr(bode, name)
+
+
+def test_klsampler_signature_matches_reference():
+    import inspect
+    sig = inspect.signature(bode_b200.KLSampler.__init__)
+    names = list(sig.parameters)
+    ref = ['self', 'X', 'Y', 'x_hyp', 'obj_func', 'noisy', 'bounds', 'true_func', 'model_kern', 'num_opt_restarts',
+           'num_mc_samples', 'num_quad_points', 'energy', 'nugget', 'lengthscale', 'variance', 'N_avg', 'kld_tol', 'func_name',
+           'quad_points', 'quad_points_weight', 'max_it', 'ekld_nugget', 'per_sampled', 'mcmc_acc_low', 'mcmc_acc_upp',
+           'mcmc_model', 'mcmc_steps', 'mcmc_final', 'ego_init_perc', 'mcmc_chains', 'mcmc_burn', 'mcmc_thin', 'mcmc_parallel',
+           'ego_iter', 'initialize_from_prior', 'variance_prior', 'lengthscale_prior', 'noise_prior', 'mcmc_model_avg']
+    assert names[:len(ref)] == ref  # reference order (bode/_sampler.py:93-127); extras come after
+    p = sig.parameters
+    assert p['nugget'].default == 1e-3 and p['max_it'].default == 50 and p['mcmc_model_avg'].default == 50
+    o = inspect.signature(bode_b200.KLSampler.optimize).parameters
+    assert list(o) == ['self', 'num_designs', 'verbose', 'plots', 'comp', 'comp_plots'] and o['num_designs'].default == 1000
+
+
+def test_lhs_center_is_a_permutation_of_cell_centres():
+    np.random.seed(1333)
+    H = _lhs.lhs(3, samples=7, criterion='center')
+    assert H.shape == (7, 3)
+    centres = (np.arange(7) + 0.5) / 7
+    for j in range(3):
+        np.testing.assert_allclose(np.sort(H[:, j]), centres, rtol=0, atol=1e-15)
+    # samp_ex1: lhs(1, 3, 'center') -> {1/6, 1/2, 5/6}
+    np.testing.assert_allclose(np.sort(_lhs.lhs(1, samples=3, criterion='center')[:, 0]), [1 / 6, 1 / 2, 5 / 6])
+
+
+def test_lhs_classic_one_point_per_cell_and_rng_order():
+    np.random.seed(7)
+    H = _lhs.lhs(2, samples=50)
+    for j in range(2):
+        assert sorted(np.floor(H[:, j] * 50).astype(int).tolist()) == list(range(50))
+    # pyDOE consumption order: rand(samples, n) first, then one permutation per column
+    np.random.seed(7)
+    u = np.random.rand(50, 2)
+    p0 = np.random.permutation(range(50))
+    a = np.linspace(0, 1, 51)[:50]
+    np.testing.assert_allclose(H[:, 0], (u[:, 0] / 50 + a)[p0])
+    with pytest.raises(ValueError):
+        _lhs.lhs(2, 5, criterion='maximin')
+
+
+def test_ensemble_sampler_moments_and_shapes():
+    np.random.seed(3)
+    mu = np.array([1.0, -2.0]); sd = np.array([0.5, 2.0])
+    lnp = lambda p: float(-0.5 * np.sum(((p - mu) / sd) ** 2))
+    s = _emcee.EnsembleSampler(10, 2, lnp)
+    p0 = mu + 0.1 * np.random.randn(10, 2)
+    s.run_mcmc(p0, 1500)
+    assert s.chain.shape == (10, 1500, 2) and s.acceptance_fraction.shape == (10,)
+    flat = s.chain[:, 300:, :].reshape(-1, 2)
+    assert np.all(np.abs(flat.mean(0) - mu) < 0.25 * sd)
+    assert np.all(np.abs(flat.std(0) / sd - 1) < 0.25)
+    assert 0.2 < s.acceptance_fraction.mean() < 0.95
+
+
+def test_ensemble_sampler_vectorised_path_is_identical():
+    mu = np.array([0.3, 0.7, 1.1])
+    lnp1 = lambda p: float(-0.5 * np.sum((p - mu) ** 2))
+    lnpv = lambda P: -0.5 * np.sum((P - mu) ** 2, axis=1)
+    out = []
+    for fn, vec in ((lnp1, False), (lnpv, True)):
+        np.random.seed(11)
+        s = _emcee.EnsembleSampler(6, 3, fn, vectorize=vec)
+        s.run_mcmc(mu + 0.05 * np.random.randn(6, 3), 50)
+        out.append(s.chain.copy())
+    np.testing.assert_array_equal(out[0], out[1])
+    with pytest.raises(ValueError):
+        _emcee.EnsembleSampler(5, 2, lnp1)
+
+
+def test_priors_sampling():
+    u = UniformPrior(a=0.2, b=0.9)
+    x = u.sample(size=100)
+    assert x.min() >= 0.2 and x.max() <= 0.9
+    assert u(0.5) == pytest.approx(-np.log(0.7)) and u(0.95) == -np.inf
+    with pytest.raises(SystemExit):
+        JeffreysPrior().sample()
+
+
+def test_shard_bounds_cover_exactly():
+    for n in (1, 7, 64, 100000, 12345):
+        for w in (1, 2, 3, 4, 8):
+            spans = [dist.shard_bounds(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            assert all(hi >= lo for lo, hi in spans)
+
+
+def test_combine_argmax_semantics():
+    t = lambda v, i: (torch.tensor(v, dtype=torch.float64), torch.tensor(i, dtype=torch.int64))
+    assert dist.combine_argmax(*t([1.0, 3.0, 2.0], [5, 17, 40])) == (3.0, 17)
+    assert dist.combine_argmax(*t([3.0, 3.0], [90, 17]))[1] == 17          # tie -> lowest global index
+    v, i = dist.combine_argmax(*t([float('nan'), 9.0, float('nan')], [30, 2, 12]))
+    assert np.isnan(v) and i == 12                                          # NaN wins, first NaN index
+    assert dist.combine_argmax(*t([float('-inf'), 1.0], [-1, 8])) == (1.0, 8)  # empty shard ignored
+    # agrees with np.argmax on random data split into shards
+    rng = np.random.default_rng(0)
+    for trial in range(50):
+        x = rng.integers(0, 6, size=37).astype(float)
+        if trial % 3 == 0:
+            x[rng.integers(0, 37, size=2)] = np.nan
+        vals, idxs = [], []
+        for r in range(4):
+            lo, hi = dist.shard_bounds(37, 4, r)
+            j = int(np.argmax(x[lo:hi]))
+            vals.append(x[lo + j]); idxs.append(lo + j)
+        assert dist.combine_argmax(*t(vals, idxs))[1] == int(np.argmax(x))

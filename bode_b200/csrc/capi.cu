@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -148,7 +149,11 @@ static int score_common(const void* workspace, int n, int d, int S, const double
   ScoreArgs a;
   a.ws = workspace; a.L = L; a.Xd = Xd; a.Nd = Nd; a.logk = logk; a.S = S;
   a.sc = P.sc; a.ntiles = P.ntiles; a.form = form; a.mode = mode;
-  a.stages = P.stages; a.chunk_max = P.chunk_max; a.nchunks = P.nchunks;
+  {
+    const char* dbg = getenv("BODE_DEBUG_SKIP");
+    a.debug_skip = dbg ? atoi(dbg) : 0;
+  }
+  a.stages = P.stages; a.chunk_max = P.chunk_max; a.nchunks = P.nchunks; a.u_global = P.u_global;
   memcpy(a.chunk_g0, P.chunk_g0, sizeof(a.chunk_g0));
   memcpy(a.tile_id, P.tile_id, sizeof(a.tile_id));
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "layout.h"
 #include "rbf.h"
@@ -52,6 +53,20 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
+// non-blocking poll (try_wait may suspend the thread for a hardware time limit; test_wait never does)
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
@@ -66,7 +81,14 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
 }
-__device__ __forceinline__ void compute_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kComputeThreads) : "memory"); }
+template <int NT>
+__device__ __forceinline__ void compute_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
+// one lane of a converged warp (no thread-id arithmetic, no S2R in hot loops)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(p));
+  return p != 0;
+}
 
 // ----------------------------------------------------------------------------------------------------------------
 // Phase A: Kc[(g*C + c)*4 + kk] = ss * exp(-sum_k (U[4g+kk][k] - x_c[k] ck[k])^2); partial w.k; partial xik factors
@@ -94,47 +116,47 @@ __device__ __forceinline__ double sqdist(const double* __restrict__ uj, const do
   return r2;
 }
 
-template <int DP, int C>
-__device__ __forceinline__ void phase_a(const double* __restrict__ aux, int aux_u_off, int dpad, int ng, int d,
+template <int DP, int C, int NT>
+__device__ __forceinline__ void phase_a(const double* __restrict__ aux, const double* __restrict__ U, int dpad, int g_lo, int g_hi, int d,
                                         const double* __restrict__ xt, double* __restrict__ Kc,
                                         double* __restrict__ pv, double* __restrict__ xip, int tid) {
-  constexpr int NJQ = kComputeThreads / C;
+  constexpr int NJQ = NT / C;
   const int c = tid % C, jq = tid / C;
   const double* ck = aux + aux_ck();
   const double* ell = aux + aux_ell();
   const double* tab = aux + aux_tab();
   const double* w = aux + aux_w();
-  const double* U = aux + aux_u_off;
   double y[DP];
 #pragma unroll
   for (int k = 0; k < DP; k++) y[k] = xt[k * C + c] * ck[k];
   double wk = 0.0;
-  int g = jq;
-  // two k4 groups (8 independent exp chains) per iteration
-  for (; g + NJQ < ng; g += 2 * NJQ) {
+  int g = g_lo;
+  // this thread slice owns the k4 groups [g_lo, g_hi); two groups (8 independent exp chains) per iteration
+  constexpr int GS = 1;  // stride between the two groups of an iteration
+  for (; g + GS < g_hi; g += 2 * GS) {
     double r2[8];
 #pragma unroll
     for (int kk = 0; kk < 4; kk++) {
       r2[kk] = sqdist<DP>(U + (size_t)(4 * g + kk) * dpad, y);
-      r2[4 + kk] = sqdist<DP>(U + (size_t)(4 * (g + NJQ) + kk) * dpad, y);
+      r2[4 + kk] = sqdist<DP>(U + (size_t)(4 * (g + GS) + kk) * dpad, y);
     }
     double kv[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) kv[i] = rbf_exp(-r2[i], tab);
     const double2 wa = *reinterpret_cast<const double2*>(w + 4 * g);
     const double2 wb = *reinterpret_cast<const double2*>(w + 4 * g + 2);
-    const double2 wc = *reinterpret_cast<const double2*>(w + 4 * (g + NJQ));
-    const double2 wd = *reinterpret_cast<const double2*>(w + 4 * (g + NJQ) + 2);
+    const double2 wc = *reinterpret_cast<const double2*>(w + 4 * (g + GS));
+    const double2 wd = *reinterpret_cast<const double2*>(w + 4 * (g + GS) + 2);
     wk = fma(wa.x, kv[0], wk); wk = fma(wa.y, kv[1], wk); wk = fma(wb.x, kv[2], wk); wk = fma(wb.y, kv[3], wk);
     wk = fma(wc.x, kv[4], wk); wk = fma(wc.y, kv[5], wk); wk = fma(wd.x, kv[6], wk); wk = fma(wd.y, kv[7], wk);
     double2* d0 = reinterpret_cast<double2*>(Kc + ((size_t)g * C + c) * 4);
     d0[0] = make_double2(kv[0], kv[1]);
     d0[1] = make_double2(kv[2], kv[3]);
-    double2* d1 = reinterpret_cast<double2*>(Kc + ((size_t)(g + NJQ) * C + c) * 4);
+    double2* d1 = reinterpret_cast<double2*>(Kc + ((size_t)(g + GS) * C + c) * 4);
     d1[0] = make_double2(kv[4], kv[5]);
     d1[1] = make_double2(kv[6], kv[7]);
   }
-  if (g < ng) {
+  if (g < g_hi) {
     double kv[4];
 #pragma unroll
     for (int kk = 0; kk < 4; kk++) kv[kk] = rbf_exp(-sqdist<DP>(U + (size_t)(4 * g + kk) * dpad, y), tab);
@@ -155,13 +177,13 @@ __device__ __forceinline__ void phase_a(const double* __restrict__ aux, int aux_
   xip[jq * C + c] = xf;
 }
 
-template <int C>
-__device__ __forceinline__ void phase_a_dispatch(const double* aux, int aux_u_off, int dpad, int ng, int d,
+template <int C, int NT>
+__device__ __forceinline__ void phase_a_dispatch(const double* aux, const double* U, int dpad, int g_lo, int g_hi, int d,
                                                  const double* xt, double* Kc, double* pv, double* xip, int tid) {
   switch (d) {
 #define BODE_CASE(D)                                                          \
   case D:                                                                     \
-    phase_a<D, C>(aux, aux_u_off, dpad, ng, d, xt, Kc, pv, xip, tid);         \
+    phase_a<D, C, NT>(aux, U, dpad, g_lo, g_hi, d, xt, Kc, pv, xip, tid);         \
     break;
     BODE_CASE(1) BODE_CASE(2) BODE_CASE(3) BODE_CASE(4) BODE_CASE(5) BODE_CASE(6) BODE_CASE(7) BODE_CASE(8)
     BODE_CASE(9) BODE_CASE(10) BODE_CASE(11) BODE_CASE(12) BODE_CASE(13) BODE_CASE(14) BODE_CASE(15) BODE_CASE(16)
@@ -172,54 +194,66 @@ __device__ __forceinline__ void phase_a_dispatch(const double* aux, int aux_u_of
 }
 
 // ----------------------------------------------------------------------------------------------------------------
-// Phase B inner loop: k4 groups [g, g_end) during which exactly the accumulator slots T0..RT-1 are live.
-// All fragment loads of a group are issued before its DMMAs (no predicates, no per-slot branches).
+// Phase B primitive: one PAIR of k4 groups (8 columns of L^-1) against the accumulator slots T0..RT-1.
+// mb points at block (row tile p, group 2p) of the staged chunk (+lane); toff[t] = 32 * (tile index of slot t);
+// gstride = doubles between group 2p and group 2p+1.  All fragment loads are issued before the DMMAs.
 // ----------------------------------------------------------------------------------------------------------------
 template <int RT, int CT, int T0>
-__device__ __forceinline__ void run_groups(double (&acc)[RT][CT][2], const int (&toff)[RT], const double* __restrict__ kc_lane,
-                                           const double* __restrict__ mb, int g, int g_end, int C, int nrt) {
-  // mb points at block (row tile g/2, group g) of the staged chunk (+lane); toff[t] = 32 * tile index of slot t
-  const double* kb = kc_lane + (size_t)g * C * 4;
-  for (; g < g_end; ++g) {
-    const int r0 = g >> 1;
-    const double* m0 = mb - r0 * 32;
-    double b[CT], a[RT - T0];
+__device__ __forceinline__ void mma_pair(double (&acc)[RT][CT][2], const int (&toff)[RT], const double* __restrict__ kb,
+                                         const double* __restrict__ m0, int gstride, int C) {
+  double b0[CT], b1[CT], a0[RT - T0], a1[RT - T0];
 #pragma unroll
-    for (int ct = 0; ct < CT; ct++) b[ct] = kb[ct * 32];
+  for (int ct = 0; ct < CT; ct++) { b0[ct] = kb[ct * 32]; b1[ct] = kb[C * 4 + ct * 32]; }
 #pragma unroll
-    for (int t = T0; t < RT; t++) a[t - T0] = m0[toff[t]];
+  for (int t = T0; t < RT; t++) { a0[t - T0] = m0[toff[t]]; a1[t - T0] = m0[gstride + toff[t]]; }
 #pragma unroll
-    for (int t = T0; t < RT; t++)
+  for (int t = T0; t < RT; t++)
 #pragma unroll
-      for (int ct = 0; ct < CT; ct++) dmma884(acc[t][ct][0], acc[t][ct][1], a[t - T0], b[ct]);
-    mb += (nrt - r0) * 32;
-    kb += C * 4;
-  }
+    for (int ct = 0; ct < CT; ct++) dmma884(acc[t][ct][0], acc[t][ct][1], a0[t - T0], b0[ct]);
+#pragma unroll
+  for (int t = T0; t < RT; t++)
+#pragma unroll
+    for (int ct = 0; ct < CT; ct++) dmma884(acc[t][ct][0], acc[t][ct][1], a1[t - T0], b1[ct]);
 }
-
-template <int RT, int CT, int T0 = 0>
-struct SegDispatch {
-  static __device__ __forceinline__ void run(int t0, double (&acc)[RT][CT][2], const int (&toff)[RT], const double* kc_lane,
-                                             const double* mb, int g, int g_end, int C, int nrt) {
-    if (t0 == T0) run_groups<RT, CT, T0>(acc, toff, kc_lane, mb, g, g_end, C, nrt);
-    else SegDispatch<RT, CT, T0 + 1>::run(t0, acc, toff, kc_lane, mb, g, g_end, C, nrt);
-  }
-};
-template <int RT, int CT>
-struct SegDispatch<RT, CT, RT> {
-  static __device__ __forceinline__ void run(int, double (&)[RT][CT][2], const int (&)[RT], const double*, const double*,
-                                             int, int, int, int) {}
-};
 
 // ----------------------------------------------------------------------------------------------------------------
 // The scoring kernel.  16 compute warps = RG row groups x CG column groups; each warp owns up to RT row tiles
 // (8 rows of T each) x CT column tiles (8 candidates each) as DMMA accumulators.  C = CG*CT*8 candidates per CTA.
 // ----------------------------------------------------------------------------------------------------------------
+// Static recursion over the number of dead accumulator slots: slot t dies at pair pend[t]; while slots T0.. are
+// live the warp runs the T0-specialised pair primitive.  The chunk transition (release the finished ring stage,
+// wait for the next) is an inline, rarely taken branch of the pair loop.
+template <int RT, int CT, int T0>
+struct PhaseB {
+  template <typename Enter, typename Leave>
+  static __device__ __forceinline__ void run(double (&acc)[RT][CT][2], const int (&toff)[RT], const int (&pend)[RT],
+                                             int& p, int& next_cp, const double*& mb, const double*& kb, int nrt, int C,
+                                             Enter&& enter, Leave&& leave) {
+    const int pe = pend[T0];
+    while (p < pe) {
+      if (p == next_cp) { leave(); enter(); }
+      const int gstride = (nrt - p) * 32;
+      mma_pair<RT, CT, T0>(acc, toff, kb, mb - p * 32, gstride, C);
+      mb += 2 * gstride;
+      kb += 2 * C * 4;
+      ++p;
+    }
+    PhaseB<RT, CT, T0 + 1>::run(acc, toff, pend, p, next_cp, mb, kb, nrt, C, enter, leave);
+  }
+};
+template <int RT, int CT>
+struct PhaseB<RT, CT, RT> {
+  template <typename Enter, typename Leave>
+  static __device__ __forceinline__ void run(double (&)[RT][CT][2], const int (&)[RT], const int (&)[RT], int&, int&,
+                                             const double*&, const double*&, int, int, Enter&&, Leave&&) {}
+};
+
 template <int RG, int CG, int RT, int CT>
-__global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constant__ ScoreArgs a) {
-  static_assert(RG * CG == kComputeWarps, "warp grid");
-  constexpr int C = CG * CT * 8;  // candidates per CTA
-  constexpr int NJQ = kComputeThreads / C;
+__global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && CT <= 2) ? 2 : 1) k_score(const __grid_constant__ ScoreArgs a) {
+  constexpr int kWarps = RG * CG;        // 16: one CTA per SM (128 registers/thread)
+  constexpr int kThreads = 32 * kWarps;
+  constexpr int C = CG * CT * 8;         // candidates per CTA
+  constexpr int NJQ = kThreads / C;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const Layout& L = a.L;
@@ -229,59 +263,40 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
   // ---- shared memory carve-up (offsets in doubles; everything 16-byte aligned) ----
   double* Kc = reinterpret_cast<double*>(smem_raw);             // [ng][C][4]
   double* auxs = Kc + (size_t)npad * C;                          // aux block of the current sample
-  double* ring = auxs + L.aux_doubles;                           // [stages][chunk_max]
+  const int aux_smem_doubles = a.u_global ? aux_u(L) : (int)L.aux_doubles;  // U may stay in global memory
+  double* ring = auxs + aux_smem_doubles;                        // [stages][chunk_max]
   double* red = ring + (size_t)stages * a.chunk_max;             // [RG][C]
-  double* pv = red + RG * C;                                     // [2][NJQ][C]   (NJQ*C = kComputeThreads)
-  double* xip = pv + 2 * kComputeThreads;                        // [2][NJQ][C]
-  double* xt = xip + 2 * kComputeThreads;                        // [kXtStride][C]  candidate tile, dimension-major
+  double* pv = red + RG * C;                                     // [2][NJQ][C]   (NJQ*C = kThreads)
+  double* xip = pv + 2 * kThreads;                               // [2][NJQ][C]
+  double* xt = xip + 2 * kThreads;                               // [kXtStride][C]  candidate tile, dimension-major
   uint64_t* bars = reinterpret_cast<uint64_t*>(xt + C * kXtStride);
-  const uint32_t full0 = smem_u32(bars);                          // full[stages]
-  const uint32_t empty0 = full0 + 8 * kMaxStages;                 // empty[stages]
+  const uint32_t full0 = smem_u32(bars);                          // full[stages]: TMA completion per ring stage
+  const uint32_t empty0 = full0 + 8 * kMaxStages;                 // empty[stages]: all warps are done with the stage
   const uint32_t aux_full = empty0 + 8 * kMaxStages;
-  const uint32_t aux_empty = aux_full + 8;
-  // per-row-group phase-B program, built once per CTA: entries (g_begin | g_end<<10 | t0<<20 | first<<26 | last<<27)
-  const int prog_stride = nchunks + kMaxRT;
-  int* prog = reinterpret_cast<int*>(bars + 2 * kMaxStages + 2);  // [RG][prog_stride]
-  int* prog_len = prog + RG * prog_stride;                        // [RG]
+  int* chunk_off = reinterpret_cast<int*>(bars + 2 * kMaxStages + 1);  // [nchunks+1] offset (doubles) of chunk q inside M_s
+  int* chunk_p0 = chunk_off + nchunks + 1;                              // [nchunks+1] first group PAIR of chunk q
 
   // ---- work item ----
   const int item = blockIdx.x;
   const int sch = item / a.ntiles, tile = item - sch * a.ntiles;
   const int s_begin = sch * a.sc, s_end = min(a.S, s_begin + a.sc);
+  const int nsamp = s_end - s_begin;
   const int64_t c0 = (int64_t)tile * C;
 
   if (tid == 0) {
     for (int i = 0; i < stages; i++) {
       mbar_init(full0 + 8 * i, 1);
-      mbar_init(empty0 + 8 * i, kComputeWarps);
+      mbar_init(empty0 + 8 * i, kWarps);
     }
     mbar_init(aux_full, 1);
-    mbar_init(aux_empty, kComputeWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (tid < RG) {
-    // segments of constant live-slot count, cut at chunk boundaries; every chunk gets at least one entry so that
-    // every warp waits on / releases every ring stage exactly once per chunk.
-    const short* tl = a.tile_id + tid * kMaxRT;
-    int* pr = prog + tid * prog_stride;
-    int np = 0, t0 = 0;
-    for (int q = 0; q < nchunks; q++) {
-      int g = a.chunk_g0[q];
-      const int g_hi = a.chunk_g0[q + 1];
-      bool first = true;
-      while (g < g_hi) {
-        while (t0 < RT && 2 * (int)tl[t0] + 2 <= g) t0++;
-        const int ge = (t0 < RT) ? min(g_hi, 2 * (int)tl[t0] + 2) : g_hi;
-        const bool last = (ge == g_hi);
-        pr[np++] = g | (ge << 10) | (t0 << 20) | ((first ? 1 : 0) << 26) | ((last ? 1 : 0) << 27);
-        first = false;
-        g = ge;
-      }
-    }
-    prog_len[tid] = np;
+  for (int q = tid; q <= nchunks; q += kThreads) {
+    chunk_off[q] = (int)m_goff(nrt, a.chunk_g0[q]);
+    chunk_p0[q] = (q < nchunks) ? (a.chunk_g0[q] >> 1) : 0x7fffffff;
   }
   // candidate tile -> smem, dimension-major (rows beyond Nd are filled with a harmless interior point)
-  for (int idx = tid; idx < C * kXtStride; idx += kScoreThreads) {
+  for (int idx = tid; idx < C * kXtStride; idx += kThreads) {
     const int k = idx / C, c = idx - k * C;
     double v = 0.5;
     if (k < L.d && c0 + c < a.Nd) v = a.Xd[(c0 + c) * L.d + k];
@@ -290,70 +305,85 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
   __syncthreads();
 
   const char* wsb = static_cast<const char*>(a.ws);
-  const double* aux_g = reinterpret_cast<const double*>(wsb + L.off_aux);
-  const double* m_g = reinterpret_cast<const double*>(wsb + L.off_m);
-  const uint32_t aux_bytes = (uint32_t)(L.aux_doubles * sizeof(double));
+  const double* aux_g = reinterpret_cast<const double*>(wsb + L.off_aux) + (size_t)s_begin * L.aux_doubles;
+  const double* m_g = reinterpret_cast<const double*>(wsb + L.off_m) + (size_t)s_begin * L.m_doubles;
+  const uint32_t aux_bytes = (uint32_t)(aux_smem_doubles * sizeof(double));
+  const uint32_t ring_u32 = smem_u32(ring), chunk_bytes_max = (uint32_t)a.chunk_max * 8u;
 
-  if (warp >= kComputeWarps) {
-    // ============================ producer warpgroup (one elected lane of its first warp) ========================
-    // Register budget: the CTA launches with 20 warps x 96 registers; this warpgroup shrinks to 24 so that the four
-    // compute warpgroups can grow to 112 out of the registers it releases (setmaxnreg is warpgroup-collective and
-    // the pool is per CTA, hence a full group of 4 warps here).
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-    if (warp == kComputeWarps && lane == 0) {
-      const uint32_t ring_u32 = smem_u32(ring), auxs_u32 = smem_u32(auxs);
-      const uint32_t chunk_bytes_max = (uint32_t)a.chunk_max * 8u;
-      int st = 0;
-      uint32_t ph = 0;  // parity of the ring round currently being filled
-      bool first_round = true;
-      for (int s = s_begin; s < s_end; s++) {
-        const int ls = s - s_begin;
-        if (ls > 0) mbar_wait(aux_empty, (uint32_t)((ls - 1) & 1));
-        mbar_arrive_expect_tx(aux_full, aux_bytes);
-        bulk_copy_g2s(auxs_u32, aux_g + (size_t)s * L.aux_doubles, aux_bytes, aux_full);
-        const double* ms = m_g + (size_t)s * L.m_doubles;
-        size_t o0 = 0;
-        for (int q = 0; q < nchunks; q++) {
-          if (!first_round) mbar_wait(empty0 + 8 * st, ph ^ 1);
-          const size_t o1 = m_goff(nrt, a.chunk_g0[q + 1]);
-          const uint32_t bytes = (uint32_t)((o1 - o0) * sizeof(double));
-          mbar_arrive_expect_tx(full0 + 8 * st, bytes);
-          bulk_copy_g2s(ring_u32 + (uint32_t)st * chunk_bytes_max, ms + o0, bytes, full0 + 8 * st);
-          o0 = o1;
-          if (++st == stages) { st = 0; ph ^= 1; first_round = false; }
-        }
-      }
+  // There is no producer warp (all 16 warps compute, 128 registers per thread).  Ring protocol per chunk `it`:
+  // every warp waits full[st] (polled one chunk ahead so the poll's latency hides under the DMMAs), computes, and
+  // arrives on empty[st] (fire and forget); the refill of the stage used by chunk it-1 is issued when chunk it is
+  // entered by warp (it-lag) % kWarps (lag = 2 chunks), by which time the other warps have released it.
+  auto issue_chunk = [&](int ls_, int q_, int st_) {
+    const uint32_t bytes = (uint32_t)(chunk_off[q_ + 1] - chunk_off[q_]) * 8u;
+    mbar_arrive_expect_tx(full0 + 8 * st_, bytes);
+    bulk_copy_g2s(ring_u32 + (uint32_t)st_ * chunk_bytes_max, m_g + (size_t)ls_ * L.m_doubles + chunk_off[q_], bytes, full0 + 8 * st_);
+  };
+  if (tid == 0) {
+    mbar_arrive_expect_tx(aux_full, aux_bytes);
+    bulk_copy_g2s(smem_u32(auxs), aux_g, aux_bytes, aux_full);
+    int ls_ = 0, q_ = 0;
+    for (int i = 0; i < stages && ls_ < nsamp; i++) {
+      issue_chunk(ls_, q_, i);
+      if (++q_ == nchunks) { q_ = 0; ls_++; }
     }
-    return;
   }
 
-  // ========================================== compute warps ======================================================
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
-  const int rg = warp % RG, cg = warp / RG;
+  // warp w runs on SM sub-partition w % 4: each sub-partition hosts the four ROW groups of one column group, so its
+  // warps have different tile sets (their bookkeeping interleaves) while it still owns exactly 1/4 of the DMMAs.
+  const int rg = warp / CG, cg = warp % CG;
   const int cbase = cg * CT * 8;
-  int toff[RT];
+  int toff[RT], pend[RT];
 #pragma unroll
-  for (int t = 0; t < RT; t++) toff[t] = 32 * (int)a.tile_id[rg * kMaxRT + t];
-  const int* my_prog = prog + rg * prog_stride;
-  const int my_len = prog_len[rg];
+  for (int t = 0; t < RT; t++) {
+    const int R = (int)a.tile_id[rg * kMaxRT + t];  // -1: unused slot
+    toff[t] = 32 * R;
+    pend[t] = R + 1;                                // slot t is live for pairs p <= R
+  }
   const double* kc_lane = Kc + (size_t)cbase * 4 + lane;
   const double* ring_lane = ring + lane;
 
   const int aux_u_off = aux_u(L);
-  int st = 0;
-  uint32_t ph = 0;
-  for (int s = s_begin; s < s_end; s++) {
-    const int ls = s - s_begin, par = ls & 1;
-    double* pvp = pv + par * kComputeThreads;
-    double* xipp = xip + par * kComputeThreads;
+  // phase-A split of the ng k4 groups over the NJQ thread slices.  Slice 0 (threads < C) also runs the per-candidate
+  // epilogue of the previous sample, a ~3000-cycle dependent chain (div, sqrt, log): it gets kEpiGroups fewer groups
+  // so that the epilogue hides under the other slices' phase A instead of delaying the post-A barrier.
+  int ga_lo, ga_hi;
+  {
+    constexpr int kEpiGroups = 3;
+    const int jq = tid / C;
+    const int n0 = (ng >= 4 * NJQ) ? max(0, ng / NJQ - kEpiGroups) : ng / NJQ;
+    const int rest = ng - n0, per = (NJQ > 1) ? rest / (NJQ - 1) : 0, extra = (NJQ > 1) ? rest - per * (NJQ - 1) : 0;
+    if (NJQ == 1) { ga_lo = 0; ga_hi = ng; }
+    else if (jq == 0) { ga_lo = 0; ga_hi = n0; }
+    else { ga_lo = n0 + (jq - 1) * per + min(jq - 1, extra); ga_hi = ga_lo + per + ((jq - 1) < extra ? 1 : 0); }
+  }
+  int st = 0, it = 0;
+  uint32_t ph = 0, ok = 0;
+  // refills trail the consumer by `lag` chunks so that the duty warp rarely has to wait for slower warps
+  const int lag = (stages >= 4) ? 2 : 1;
+  // refill cursor: (sample, chunk) that goes into the stage released by chunk it-lag, i.e. chunk it-lag+stages
+  int rf_ls = 0, rf_q = 0;
+  for (int i = 0; i < stages; i++) if (++rf_q == nchunks) { rf_q = 0; rf_ls++; }
+
+  for (int ls = 0; ls < nsamp; ls++) {
+    const int par = ls & 1;
+    double* pvp = pv + par * kThreads;
+    double* xipp = xip + par * kThreads;
     // ---- phase A ----
     mbar_wait(aux_full, (uint32_t)par);
     double ss = 0, noise = 0, sigma1 = 0;
     if (tid < C) { ss = auxs[C_SS]; noise = auxs[C_NOISE]; sigma1 = auxs[C_SIGMA1]; }
-    phase_a_dispatch<C>(auxs, aux_u_off, L.dpad, ng, L.d, xt, Kc, pvp, xipp, tid);
-    __syncwarp();
-    if (lane == 0) mbar_arrive(aux_empty);
-    compute_bar_sync();
+    if (!((a.debug_skip & 1) && ls > 0)) {
+      // two call sites so that the U loads stay address-space specific (LDS vs LDG) instead of generic
+      if (a.u_global) phase_a_dispatch<C, kThreads>(auxs, aux_g + (size_t)ls * L.aux_doubles + aux_u_off, L.dpad, ga_lo, ga_hi, L.d, xt, Kc, pvp, xipp, tid);
+      else phase_a_dispatch<C, kThreads>(auxs, auxs + aux_u_off, L.dpad, ga_lo, ga_hi, L.d, xt, Kc, pvp, xipp, tid);
+    }
+    __syncthreads();
+    // every warp is done with the aux block: fetch the next sample's while phase B runs
+    if (tid == 0 && ls + 1 < nsamp) {
+      mbar_arrive_expect_tx(aux_full, aux_bytes);
+      bulk_copy_g2s(smem_u32(auxs), aux_g + (size_t)(ls + 1) * L.aux_doubles, aux_bytes, aux_full);
+    }
 
     // ---- phase B: T = L^-1 Kc on the FP64 tensor pipe ----
     double acc[RT][CT][2];
@@ -362,28 +392,38 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
 #pragma unroll
       for (int ct = 0; ct < CT; ct++) { acc[t][ct][0] = 0.0; acc[t][ct][1] = 0.0; }
 
+    int q = -1, p = 0, next_cp = 0;
     const double* mb = ring_lane;
-    for (int i = 0; i < my_len; i++) {
-      const int e = my_prog[i];
-      const int g = e & 1023, ge = (e >> 10) & 1023, t0 = (e >> 20) & 63;
-      if (e & (1 << 26)) {
-        mbar_wait(full0 + 8 * st, ph);
-        mb = ring_lane + (size_t)st * a.chunk_max;
-      }
-      SegDispatch<RT, CT>::run(t0, acc, toff, kc_lane, mb, g, ge, C, nrt);
-      // advance mb over the groups [g, ge) of this chunk: sum_{g'} (nrt - g'/2) blocks
-      {
-        const int a0 = g >> 1, a1 = ge >> 1;  // closed form of sum_{g'=g}^{ge-1} (nrt - (g' >> 1))
-        const int full_pairs = 2 * ((a1 - a0) * nrt - (a1 * (a1 - 1) - a0 * (a0 - 1)) / 2);
-        const int adj = ((ge & 1) ? (nrt - a1) : 0) - ((g & 1) ? (nrt - a0) : 0);
-        mb += (full_pairs + adj) * 32;
-      }
-      if (e & (1 << 27)) {
+    const double* kb = kc_lane;
+    auto enter = [&]() {  // start chunk q+1 (ring stage st)
+      ++q;
+      if (it >= lag && ((it - lag) & (kWarps - 1)) == warp) {
+        // refill duty for the stage released `lag` chunks ago (chunk it-lag -> chunk it-lag+stages)
+        if (rf_ls < nsamp && elect_one()) {
+          const int pst = (st >= lag) ? st - lag : st - lag + stages;
+          mbar_wait(empty0 + 8 * pst, (st >= lag) ? ph : (ph ^ 1));
+          issue_chunk(rf_ls, rf_q, pst);
+        }
         __syncwarp();
-        if (lane == 0) mbar_arrive(empty0 + 8 * st);
-        if (++st == stages) { st = 0; ph ^= 1; }
       }
-    }
+      if (it >= lag) { if (++rf_q == nchunks) { rf_q = 0; rf_ls++; } }
+      while (!ok) ok = mbar_try_wait(full0 + 8 * st, ph);
+      mb = ring_lane + (size_t)st * a.chunk_max;
+      next_cp = chunk_p0[q + 1];
+      // look one chunk ahead with a non-blocking poll
+      const int nst = (st + 1 == stages) ? 0 : st + 1;
+      ok = mbar_test_wait(full0 + 8 * nst, (st + 1 == stages) ? (ph ^ 1) : ph);
+    };
+    auto leave = [&]() {  // done with chunk q
+      __syncwarp();
+      if (elect_one()) mbar_arrive(empty0 + 8 * st);
+      if (++st == stages) { st = 0; ph ^= 1; }
+      ++it;
+    };
+    enter();
+    if (!(a.debug_skip & 2)) PhaseB<RT, CT, 0>::run(acc, toff, pend, p, next_cp, mb, kb, nrt, C, enter, leave);
+    while (q + 1 < nchunks) { leave(); enter(); }  // chunks past this warp's last live row tile
+    leave();
 
     // ---- column sums of squares over this warp's rows -> red[rg][c] ----
 #pragma unroll
@@ -404,7 +444,7 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
         red[rg * C + cbase + ct * 8 + 2 * lane + 1] = p1;
       }
     }
-    compute_bar_sync();
+    __syncthreads();
 
     // ---- K4 epilogue: one thread per candidate ----
     if (tid < C) {
@@ -433,7 +473,7 @@ __global__ void __launch_bounds__(kScoreThreads, 1) k_score(const __grid_constan
         }
         outv = log(kld);  // :492 np.log(kld_j)
       }
-      if (c0 + tid < a.Nd) a.logk[(size_t)s * a.Nd + c0 + tid] = outv;
+      if (c0 + tid < a.Nd) a.logk[(size_t)(s_begin + ls) * a.Nd + c0 + tid] = outv;
     }
   }
 }
@@ -524,10 +564,11 @@ __global__ void k_exp_inplace(double* __restrict__ v, size_t n) {
 // ----------------------------------------------------------------------------------------------------------------
 // Host-side planning and launch
 // ----------------------------------------------------------------------------------------------------------------
-static size_t score_smem_bytes(const Layout& L, int C, int RG, int stages, int chunk_max, int nchunks) {
-  size_t dbl = (size_t)L.npad * C + L.aux_doubles + (size_t)stages * chunk_max + (size_t)RG * C + 4 * kComputeThreads +
+static size_t score_smem_bytes(const Layout& L, int C, int RG, int nthreads, int stages, int chunk_max, int nchunks, int u_global) {
+  size_t dbl = (size_t)L.npad * C + (u_global ? (size_t)aux_u(L) : L.aux_doubles) + (size_t)stages * chunk_max + (size_t)RG * C + 4 * (size_t)nthreads +
                (size_t)C * kXtStride;
-  return dbl * sizeof(double) + sizeof(uint64_t) * (2 * kMaxStages + 2) + sizeof(int) * ((size_t)RG * (nchunks + kMaxRT) + kMaxRG + 8) + 128;
+  return dbl * sizeof(double) + sizeof(uint64_t) * (2 * kMaxStages + 1) +
+         sizeof(int) * (2 * (nchunks + 1) + 8) + 128;
 }
 
 // Longest-processing-time assignment of row tiles (weight R+1 ~ number of live k4 groups) to the row groups.
@@ -549,18 +590,15 @@ static void assign_tiles(int nrt, int nrg, int rt_cap, short* tile_id /*[kMaxRG]
     for (int t = 0; t < cnt[g]; t++) tile_id[g * kMaxRT + (rt_cap - 1 - t)] = tmp[g][t];
 }
 
-int plan_score(const Layout& L, int64_t Nd, int sm_count, size_t smem_optin, ScorePlan* P) {
+static int plan_variant(const Layout& L, size_t smem_limit, ScorePlan* P) {
   const int nrt = L.nrt;
-  if (nrt <= 32) { P->variant = 0; P->rg = 4; P->cg = 4; P->rt = 8; P->ct = 2; }
-  else if (nrt <= 64) { P->variant = 1; P->rg = 4; P->cg = 4; P->rt = 16; P->ct = 1; }
-  else if (nrt <= 128) { P->variant = 2; P->rg = 8; P->cg = 2; P->rt = 16; P->ct = 1; }
-  else return -1;
   const int C = P->cg * P->ct * 8;
   P->C = C;
-  // chunk plan: consecutive k4 groups, greedily packed up to the chunk size
-  const size_t g0_doubles = (size_t)nrt * 32;
+  // chunk plan: consecutive PAIRS of k4 groups (both groups of a pair share their first stored row tile), greedily
+  // packed up to the chunk size
+  const size_t pair0_doubles = (size_t)nrt * 64;
   size_t chunk_max = 2048;  // 16 KB
-  if (chunk_max < g0_doubles) chunk_max = g0_doubles;
+  if (chunk_max < pair0_doubles) chunk_max = pair0_doubles;
   int nch = 0;
   int g = 0;
   P->chunk_g0[0] = 0;
@@ -568,10 +606,10 @@ int plan_score(const Layout& L, int64_t Nd, int sm_count, size_t smem_optin, Sco
     size_t acc = 0;
     int g1 = g;
     while (g1 < L.ng) {
-      const size_t gs = (size_t)(nrt - (g1 >> 1)) * 32;
+      const size_t gs = (size_t)(nrt - (g1 >> 1)) * 64;
       if (acc + gs > chunk_max && g1 > g) break;
       acc += gs;
-      g1++;
+      g1 += 2;
     }
     g = g1;
     P->chunk_g0[++nch] = (unsigned short)g;
@@ -579,12 +617,45 @@ int plan_score(const Layout& L, int64_t Nd, int sm_count, size_t smem_optin, Sco
   }
   P->nchunks = nch;
   P->chunk_max = (int)chunk_max;
-  int stages = kMaxStages;
-  while (stages >= 2 && score_smem_bytes(L, C, P->rg, stages, (int)chunk_max, nch) > smem_optin) stages--;
-  if (stages < 2) return -1;
-  if (stages > nch + 1 && nch + 1 >= 2) stages = nch + 1;
+  const int nthreads = 32 * P->rg * P->cg;
+  int stages = kMaxStages, u_global = 0;
+  while (stages >= 2 && score_smem_bytes(L, C, P->rg, nthreads, stages, (int)chunk_max, nch, 0) > smem_limit) stages--;
+  if (stages < 2) {  // large n: leave the prescaled observations in global memory (read through L1/L2 in phase A)
+    u_global = 1;
+    stages = kMaxStages;
+    while (stages >= 2 && score_smem_bytes(L, C, P->rg, nthreads, stages, (int)chunk_max, nch, 1) > smem_limit) stages--;
+    if (stages < 2) return -1;
+  }
+  if (stages > nch + 1) stages = nch + 1;
+  if (stages < 2) stages = 2;
+  P->u_global = u_global;
   P->stages = stages;
-  P->smem = score_smem_bytes(L, C, P->rg, stages, (int)chunk_max, nch);
+  P->smem = score_smem_bytes(L, C, P->rg, nthreads, stages, (int)chunk_max, nch, u_global);
+  return 0;
+}
+
+int plan_score(const Layout& L, int64_t Nd, int sm_count, size_t smem_optin, ScorePlan* P) {
+  const int nrt = L.nrt;
+  // BODE_SCORE_VARIANT=3|4 select experimental configurations for n <= 256 (tuning knob)
+  const char* env = getenv("BODE_SCORE_VARIANT");
+  const int forced = env ? atoi(env) : -1;
+  struct Cand { int variant, rg, cg, rt, ct; size_t limit; };
+  const Cand cands[] = {
+      {4, 4, 2, 8, 4, smem_optin}, {3, 4, 2, 8, 2, (228 * 1024) / 2 - 1024},  // only when forced
+      {0, 4, 4, 8, 2, smem_optin},    // n <= 256 : 64 candidates per CTA
+      {1, 4, 4, 16, 1, smem_optin},   // n <= 512 : 32 candidates per CTA
+      {2, 8, 2, 16, 1, smem_optin},   // n <= 1024: 16 candidates per CTA
+      {5, 16, 1, 8, 1, smem_optin},   // n <= 1024:  8 candidates per CTA (largest L^-1 chunks)
+  };
+  bool ok = false;
+  for (const Cand& c : cands) {
+    if ((c.variant == 3 || c.variant == 4) && forced != c.variant) continue;
+    if (nrt > c.rg * c.rt) continue;
+    P->variant = c.variant; P->rg = c.rg; P->cg = c.cg; P->rt = c.rt; P->ct = c.ct;
+    if (plan_variant(L, c.limit, P) == 0) { ok = true; break; }
+  }
+  if (!ok) return -1;
+  const int C = P->C;
   assign_tiles(nrt, P->rg, P->rt, P->tile_id);
   // work items: (tile, sample chunk); aim for >= 16 waves of CTAs, keep at least 4 samples per item when possible
   const int64_t ntiles = (Nd + C - 1) / C;
@@ -604,12 +675,15 @@ template <int RG, int CG, int RT, int CT>
 static cudaError_t launch_one(const ScoreArgs& a, const ScorePlan& P, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(k_score<RG, CG, RT, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem);
   if (e != cudaSuccess) return e;
-  k_score<RG, CG, RT, CT><<<(unsigned)P.nitems, kScoreThreads, P.smem, st>>>(a);
+  k_score<RG, CG, RT, CT><<<(unsigned)P.nitems, 32 * RG * CG, P.smem, st>>>(a);
   return cudaGetLastError();
 }
 
 cudaError_t launch_score(const ScoreArgs& a, const ScorePlan& P, cudaStream_t st) {
   if (P.variant == 0) return launch_one<4, 4, 8, 2>(a, P, st);
+  if (P.variant == 3) return launch_one<4, 2, 8, 2>(a, P, st);
+  if (P.variant == 4) return launch_one<4, 2, 8, 4>(a, P, st);
+  if (P.variant == 5) return launch_one<16, 1, 8, 1>(a, P, st);
   if (P.variant == 1) return launch_one<4, 4, 16, 1>(a, P, st);
   return launch_one<8, 2, 16, 1>(a, P, st);
 }

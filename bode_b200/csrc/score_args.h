@@ -12,7 +12,7 @@ constexpr int kComputeThreads = kComputeWarps * 32;  // 512
 constexpr int kScoreThreads = kComputeThreads + 128;  // + one producer warpgroup (1 active warp)
 constexpr int kMaxStages = 8;
 constexpr int kMaxRT = 16;      // row tiles per warp row-group
-constexpr int kMaxRG = 8;       // row groups
+constexpr int kMaxRG = 16;      // row groups
 constexpr int kMaxChunks = 256;
 constexpr int kMaxProg = kMaxChunks + kMaxRT;  // phase-B program entries per row group
 constexpr int kXtStride = 16;   // BODE_MAX_D doubles per candidate row in shared memory
@@ -29,17 +29,19 @@ struct ScoreArgs {
   int sc;            // hyper-samples per work item
   int ntiles;        // candidate tiles
   int form, mode;
+  int debug_skip;    // developer timing knob (env BODE_DEBUG_SKIP): 1 = skip phase A after the first sample, 2 = skip phase B's DMMAs
   int stages, chunk_max /* doubles */, nchunks;
+  int u_global;      // 1: the prescaled observations U stay in global memory (large n: they do not fit in smem)
   unsigned short chunk_g0[kMaxChunks + 1];
   short tile_id[kMaxRG * kMaxRT];  // [rg][slot], right-aligned ascending, -1 = unused
 };
 
 struct ScorePlan {
-  int variant;  // 0: n<=256 (RG4 CG4 RT8 CT2), 1: n<=512 (RG4 CG4 RT16 CT1), 2: n<=1024 (RG8 CG2 RT16 CT1)
+  int variant;  // 0: n<=256 (RG4 CG4 RT8 CT2), 1: n<=512 (RG4 CG4 RT16 CT1), 2: RG8 CG2 RT16 CT1, 5: RG16 CG1 RT8 CT1 (n<=1024)
   int rg, cg, rt, ct, C;
   int sc, ntiles;
   int64_t nitems;
-  int stages, chunk_max, nchunks;
+  int stages, chunk_max, nchunks, u_global;
   size_t smem;
   unsigned short chunk_g0[kMaxChunks + 1];
   short tile_id[kMaxRG * kMaxRT];

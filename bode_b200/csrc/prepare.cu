@@ -42,57 +42,48 @@ __device__ __forceinline__ double block_sum_ordered(double v, double* red) {
 }
 
 // P[c] -= sum_{k in [k0,k1)} row[k] * Ljp[k][c]   (Ljp staged in smem as [k][8])
-__device__ __forceinline__ void panel_gemm_row(double (&P)[kNB], const double* __restrict__ row, const double* Ljp,
-                                               int k0, int k1) {
-  int k = k0;
-  // peel to even k for 16-byte loads of the own row
-  if ((k & 1) && k < k1) {
-    const double r = row[k];
-    const double2* lp = reinterpret_cast<const double2*>(Ljp + (size_t)k * kNB);
+// The own-row operand comes from global memory (L2): it is fetched 16 columns at a time so that eight 16-byte loads
+// are in flight per thread -- the loop is bound by that latency, not by the FMAs.
+__device__ __forceinline__ void gemm_step(double (&P)[kNB], double r, const double* __restrict__ lrow) {
+  const double2* lp = reinterpret_cast<const double2*>(lrow);
 #pragma unroll
-    for (int c2 = 0; c2 < kNB / 2; c2++) {
-      const double2 l = lp[c2];
-      P[2 * c2] = fma(-r, l.x, P[2 * c2]);
-      P[2 * c2 + 1] = fma(-r, l.y, P[2 * c2 + 1]);
-    }
-    k++;
-  }
-  for (; k + 1 < k1; k += 2) {
-    const double2 r = *reinterpret_cast<const double2*>(row + k);
-    const double2* lp = reinterpret_cast<const double2*>(Ljp + (size_t)k * kNB);
-#pragma unroll
-    for (int c2 = 0; c2 < kNB / 2; c2++) {
-      const double2 l = lp[c2];
-      P[2 * c2] = fma(-r.x, l.x, P[2 * c2]);
-      P[2 * c2 + 1] = fma(-r.x, l.y, P[2 * c2 + 1]);
-    }
-#pragma unroll
-    for (int c2 = 0; c2 < kNB / 2; c2++) {
-      const double2 l = lp[kNB / 2 + c2];
-      P[2 * c2] = fma(-r.y, l.x, P[2 * c2]);
-      P[2 * c2 + 1] = fma(-r.y, l.y, P[2 * c2 + 1]);
-    }
-  }
-  if (k < k1) {
-    const double r = row[k];
-    const double2* lp = reinterpret_cast<const double2*>(Ljp + (size_t)k * kNB);
-#pragma unroll
-    for (int c2 = 0; c2 < kNB / 2; c2++) {
-      const double2 l = lp[c2];
-      P[2 * c2] = fma(-r, l.x, P[2 * c2]);
-      P[2 * c2 + 1] = fma(-r, l.y, P[2 * c2 + 1]);
-    }
+  for (int c2 = 0; c2 < kNB / 2; c2++) {
+    const double2 l = lp[c2];
+    P[2 * c2] = fma(-r, l.x, P[2 * c2]);
+    P[2 * c2 + 1] = fma(-r, l.y, P[2 * c2 + 1]);
   }
 }
 
-// x = P * Ld^-T for the 8x8 lower-triangular diagonal block Ld (smem, row-major [c][c'])
-__device__ __forceinline__ void panel_trsm_row(double (&P)[kNB], const double* Ld) {
+__device__ __forceinline__ void panel_gemm_row(double (&P)[kNB], const double* __restrict__ row, const double* Ljp,
+                                               int k0, int k1) {
+  int k = k0;
+  while ((k & 15) && k < k1) {  // peel to a 128-byte boundary of the row
+    gemm_step(P, row[k], Ljp + (size_t)k * kNB);
+    k++;
+  }
+  for (; k + 16 <= k1; k += 16) {
+    double2 r[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = *reinterpret_cast<const double2*>(row + k + 2 * i);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      gemm_step(P, r[i].x, Ljp + (size_t)(k + 2 * i) * kNB);
+      gemm_step(P, r[i].y, Ljp + (size_t)(k + 2 * i + 1) * kNB);
+    }
+  }
+  for (; k < k1; k++) gemm_step(P, row[k], Ljp + (size_t)k * kNB);
+}
+
+// x = P * Ld^-T for the 8x8 lower-triangular diagonal block Ld (smem, row-major [c][c']); rdiag[c] = 1 / Ld[c][c]
+// (eight dependent FP64 divisions per row per panel would dominate the panel's latency; the reciprocal costs one
+// extra rounding of 2^-53 per entry, well inside the factorisation's backward error)
+__device__ __forceinline__ void panel_trsm_row(double (&P)[kNB], const double* Ld, const double* rdiag) {
 #pragma unroll
   for (int c = 0; c < kNB; c++) {
     double t = P[c];
 #pragma unroll
     for (int cc = 0; cc < c; cc++) t = fma(-P[cc], Ld[c * kNB + cc], t);
-    P[c] = t / Ld[c * kNB + c];
+    P[c] = t * rdiag[c];
   }
 }
 
@@ -102,7 +93,8 @@ __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
   const int n = a.n, d = a.d, npad = a.L.npad;
   double* Ljp = sm;                        // [npad][8] staged panel rows
   double* Ld = Ljp + (size_t)npad * kNB;   // [8][8] diagonal block
-  double* red = Ld + kNB * kNB;            // [8] reduction scratch
+  double* rdiag = Ld + kNB * kNB;          // [8] reciprocals of the diagonal of Ld
+  double* red = rdiag + kNB;               // [8] reduction scratch
   double* ck = red + 8;                    // [16]
   double* tab = ck + kCkPad;               // [32] variance * 2^(j/32)
   double* vec = tab + kTabPad;             // [npad] back-substitution right-hand side
@@ -157,14 +149,21 @@ __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
   __syncthreads();
   // ---- A = K + (noise + jitter) I, lower triangle, rows 0..n-1 ------------------------------------------------
   // strictly-lower entries, flat triangular index so that all threads carry the same number of exp() calls
+  // (U is staged in the panel buffer, free until the factorisation starts, when it fits: the entries are gathers)
+  const bool u_smem = dpad <= kNB;
+  if (u_smem) {
+    for (int idx = tid; idx < npad * dpad; idx += kPrepThreads) Ljp[idx] = U[idx];
+    __syncthreads();
+  }
+  const double* Us = u_smem ? Ljp : U;
   const int ntri = n * (n - 1) / 2;
   for (int idx = tid; idx < ntri; idx += kPrepThreads) {
     int i = (int)((1.0 + sqrt(1.0 + 8.0 * (double)idx)) * 0.5);
     while (i * (i - 1) / 2 > idx) i--;
     while ((i + 1) * i / 2 <= idx) i++;
     const int j = idx - i * (i - 1) / 2;
-    const double* ui = U + (size_t)i * dpad;
-    const double* uj = U + (size_t)j * dpad;
+    const double* ui = Us + (size_t)i * dpad;
+    const double* uj = Us + (size_t)j * dpad;
     double r2 = 0.0;
     for (int k = 0; k < d; k++) {
       const double t = ui[k] - uj[k];
@@ -229,6 +228,7 @@ __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
 #pragma unroll
         for (int cc = 0; cc < kNB; cc++) {
           Ld[c * kNB + cc] = (cc <= c) ? B[cc] : 0.0;
+          if (cc == c) rdiag[c] = 1.0 / B[cc];
           if (c < nb && cc <= c && cc < nb) Lw[(size_t)(j0 + c) * npad + j0 + cc] = B[cc];
         }
       }
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
       double P[kNB];
 #pragma unroll
       for (int c = 0; c < kNB; c++) P[c] = (c < nb) ? row[j0 + c] : 0.0;
-      panel_trsm_row(P, Ld);
+      panel_trsm_row(P, Ld, rdiag);
 #pragma unroll
       for (int c = 0; c < kNB; c++)
         if (c < nb) row[j0 + c] = P[c];
@@ -299,13 +299,18 @@ __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
   __syncthreads();
   for (int j0 = ((n - 1) / kNB) * kNB; j0 >= 0; j0 -= kNB) {
     const int nb = min(kNB, n - j0);
+    if (tid < kNB * kNB) {
+      const int c = tid / kNB, cc = tid % kNB;
+      Ld[tid] = (c < nb && cc <= c) ? Lw[(size_t)(j0 + c) * npad + j0 + cc] : ((c == cc) ? 1.0 : 0.0);
+    }
+    __syncthreads();
     if (tid == 0) {
-      // solve Ld^T w_blk = vec_blk sequentially (8x8), Ld = L[j0.., j0..]
+      // solve Ld^T w_blk = vec_blk sequentially (8x8), Ld = L[j0.., j0..] staged in smem
       double wb[kNB];
       for (int c = nb - 1; c >= 0; c--) {
         double t = vec[j0 + c];
-        for (int c2 = c + 1; c2 < nb; c2++) t = fma(-Lw[(size_t)(j0 + c2) * npad + j0 + c], wb[c2], t);
-        wb[c] = t / Lw[(size_t)(j0 + c) * npad + j0 + c];
+        for (int c2 = c + 1; c2 < nb; c2++) t = fma(-Ld[c2 * kNB + c], wb[c2], t);
+        wb[c] = t / Ld[c * kNB + c];
       }
       for (int c = 0; c < nb; c++) vec[j0 + c] = wb[c];
     }
@@ -330,7 +335,9 @@ __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
     }
     if (tid < kNB * kNB) {
       const int c = tid / kNB, cc = tid % kNB;
-      Ld[tid] = (c < nb && cc <= c) ? Lw[(size_t)(j0 + c) * npad + j0 + cc] : ((c == cc) ? 1.0 : 0.0);
+      const double v = (c < nb && cc <= c) ? Lw[(size_t)(j0 + c) * npad + j0 + cc] : ((c == cc) ? 1.0 : 0.0);
+      Ld[tid] = v;
+      if (c == cc) rdiag[c] = 1.0 / v;
     }
     __syncthreads();
     for (int r = tid; r < j0 + nb; r += kPrepThreads) {
@@ -339,7 +346,7 @@ __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
 #pragma unroll
       for (int c = 0; c < kNB; c++) P[c] = (r == j0 + c) ? 1.0 : 0.0;
       if (r < j0) panel_gemm_row(P, row, Ljp, r, j0);
-      panel_trsm_row(P, Ld);
+      panel_trsm_row(P, Ld, rdiag);
 #pragma unroll
       for (int c = 0; c < kNB; c++)
         if (c < nb) row[j0 + c] = P[c];
@@ -364,7 +371,7 @@ __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
 }
 
 size_t prepare_smem_bytes(const Layout& L) {
-  return sizeof(double) * ((size_t)L.npad * kNB + kNB * kNB + 8 + kCkPad + kTabPad + L.npad);
+  return sizeof(double) * ((size_t)L.npad * kNB + kNB * kNB + kNB + 8 + kCkPad + kTabPad + L.npad);
 }
 
 cudaError_t launch_prepare(const PrepArgs& a, cudaStream_t st) {

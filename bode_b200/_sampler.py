@@ -79,7 +79,8 @@ class KLSampler(object):
                  engine=None,
                  ekld_form=0,
                  hyper_samples=None,
-                 process_group=None):
+                 process_group=None,
+                 ekld_mode='closed'):
         X = np.asarray(X, dtype=np.float64)
         Y = np.asarray(Y, dtype=np.float64)
         assert X.ndim == 2
@@ -124,6 +125,9 @@ class KLSampler(object):
         self._ego_seq = (1 - ego_init_perc) * self.ego_iter
         self.X_design = None if X_design is None else np.ascontiguousarray(X_design, dtype=np.float64)
         self.ekld_form = ekld_form
+        if ekld_mode not in ('closed', 'quad'):
+            raise ValueError("ekld_mode must be 'closed' (reference closed-form integrals) or 'quad' (quadrature points)")
+        self.ekld_mode = ekld_mode
         self.process_group = process_group
         # hyper_samples: optional callable (X, Y, it) -> ndarray (S, d+1|d+2) replacing the host MCMC (used by the
         # parity tests so that the CPU oracle and the GPU path see identical hyper-samples every iteration).
@@ -223,8 +227,19 @@ class KLSampler(object):
         return [samples_thin[:, -keep:, :].reshape((-1, ndim))]
 
     # ---- acquisition -----------------------------------------------------------------------------------------
+    def _quad(self):
+        """(X_quad, weights) in quadrature mode: the drivers' ``quad_points`` / ``quad_points_weight`` (unused by the
+        reference's EKLD path, which integrates in closed form; used here when ``ekld_mode='quad'``)."""
+        if self.ekld_mode != 'quad':
+            return None
+        q = np.asarray(self.quad_points, dtype=np.float64)
+        if q.ndim == 1:
+            q = q.reshape(-1, 1) if self.X.shape[1] == 1 else q.reshape(1, -1)
+        w = np.asarray(self.quad_points_weight, dtype=np.float64)
+        return q, (None if w.ndim != 1 else w)
+
     def _prepare(self, model, X, Y):
-        info = self.engine.prepare(X, Y, model[0], self.nugget ** 2)
+        info = self.engine.prepare(X, Y, model[0], self.nugget ** 2, quad=self._quad())
         return info
 
     def get_mu_sigma(self, model, X, Y):

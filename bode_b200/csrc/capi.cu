@@ -24,6 +24,11 @@ cudaError_t launch_reduce(const double* logk, int S, int64_t Nd, int64_t idx_off
                           double* part_val, int64_t* part_idx, double* best, int64_t* best_idx, cudaStream_t st);
 cudaError_t launch_exp_inplace(double* v, size_t n, cudaStream_t st);
 cudaError_t measure_fp64_peak(double* dmma, double* dfma);
+cudaError_t launch_rowmean(const double* hyp, int S, int ndim, int d, const double* P, int64_t Np, const double* Xq,
+                           const double* wq, int Nq, const double* wsum_ptr, double* out, cudaStream_t st);
+cudaError_t launch_weighted_mean(const double* rm, const double* wq, int Nq, const double* wsum_ptr, int S, double* out,
+                                 cudaStream_t st);
+cudaError_t launch_sum_weights(const double* wq, int Nq, double* out, cudaStream_t st);
 }  // namespace bode
 
 using namespace bode;
@@ -108,8 +113,60 @@ int bode_ekld_prepare_dev(const double* X, const double* Y, const double* hyp, i
   a.ws = static_cast<char*>(workspace);
   a.L = make_layout(n, d, S);
   a.info = info;
+  a.e_ovr = nullptr;
+  a.sigma0_ovr = nullptr;
   if (workspace_bytes < a.L.total_bytes || (reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return BODE_ERR_WORKSPACE;
   BODE_CUDA(launch_prepare(a, static_cast<cudaStream_t>(stream)));
+  return BODE_OK;
+}
+
+size_t bode_quad_scratch_bytes(int n, int S, int Nq) {
+  if (n < 1 || S < 1 || Nq < 1) return 0;
+  // [wsum (256 B)] [e: S*n] [rowmean of X_quad: S*Nq] [sigma0: S]
+  return 256 + align_up(sizeof(double) * (size_t)S * n, 256) + align_up(sizeof(double) * (size_t)S * Nq, 256) +
+         align_up(sizeof(double) * (size_t)S, 256);
+}
+
+int bode_quad_rowmean_dev(const double* hyp, int S, int ndim, int d, const double* P, int64_t Np, const double* Xq,
+                          const double* wq, int Nq, double* out, void* scratch, void* stream) {
+  if (!hyp || !P || !Xq || !out || !scratch || S < 1 || d < 1 || Np < 1 || Nq < 1) return BODE_ERR_BAD_ARG;
+  if (ndim != d + 1 && ndim != d + 2) return BODE_ERR_BAD_ARG;
+  if (d > BODE_MAX_D) return BODE_ERR_UNSUPPORTED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double* wsum = static_cast<double*>(scratch);
+  if (wq) BODE_CUDA(launch_sum_weights(wq, Nq, wsum, st));
+  BODE_CUDA(launch_rowmean(hyp, S, ndim, d, P, Np, Xq, wq, Nq, wq ? wsum : nullptr, out, st));
+  return BODE_OK;
+}
+
+int bode_ekld_prepare_quad_dev(const double* X, const double* Y, const double* hyp, int n, int d, int S, int ndim,
+                               double nugget_var, double jitter, const double* Xq, const double* wq, int Nq,
+                               void* workspace, size_t workspace_bytes, int* info, void* scratch, void* stream) {
+  if (!X || !Y || !hyp || !workspace || !info || !Xq || !scratch || !shape_ok(n, d, S) || Nq < 1) return BODE_ERR_BAD_ARG;
+  if (ndim != d + 1 && ndim != d + 2) return BODE_ERR_BAD_ARG;
+  if (!shape_supported(n, d)) return BODE_ERR_UNSUPPORTED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* sc = static_cast<char*>(scratch);
+  double* wsum = reinterpret_cast<double*>(sc);
+  double* e = reinterpret_cast<double*>(sc + 256);
+  double* rmq = reinterpret_cast<double*>(sc + 256 + align_up(sizeof(double) * (size_t)S * n, 256));
+  double* s0 = reinterpret_cast<double*>(sc + 256 + align_up(sizeof(double) * (size_t)S * n, 256) +
+                                         align_up(sizeof(double) * (size_t)S * Nq, 256));
+  if (wq) BODE_CUDA(launch_sum_weights(wq, Nq, wsum, st));
+  const double* wsp = wq ? wsum : nullptr;
+  BODE_CUDA(launch_rowmean(hyp, S, ndim, d, X, n, Xq, wq, Nq, wsp, e, st));      // e_q = mean_q k(X, x_q)
+  BODE_CUDA(launch_rowmean(hyp, S, ndim, d, Xq, Nq, Xq, wq, Nq, wsp, rmq, st));  // mean_q' k(x_q, x_q')
+  BODE_CUDA(launch_weighted_mean(rmq, wq, Nq, wsp, S, s0, st));                  // sigma0_q
+  PrepArgs a;
+  a.X = X; a.Y = Y; a.hyp = hyp; a.n = n; a.d = d; a.S = S; a.ndim = ndim;
+  a.nugget_var = nugget_var; a.jitter = jitter;
+  a.ws = static_cast<char*>(workspace);
+  a.L = make_layout(n, d, S);
+  a.info = info;
+  a.e_ovr = e;
+  a.sigma0_ovr = s0;
+  if (workspace_bytes < a.L.total_bytes || (reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return BODE_ERR_WORKSPACE;
+  BODE_CUDA(launch_prepare(a, st));
   return BODE_OK;
 }
 
@@ -134,8 +191,8 @@ size_t bode_ekld_score_scratch_bytes(int64_t Nd) {
 }
 
 static int score_common(const void* workspace, int n, int d, int S, const double* Xd, int64_t Nd, int64_t idx_offset,
-                        int form, int mode, double* logk, double* score, double* var, double* best, int64_t* best_idx,
-                        void* scratch, void* stream, float* kernel_ms) {
+                        int form, int mode, const double* xi_ovr, double* logk, double* score, double* var, double* best,
+                        int64_t* best_idx, void* scratch, void* stream, float* kernel_ms) {
   if (!workspace || !Xd || !logk || !score || !best || !best_idx || !scratch || !shape_ok(n, d, S) || Nd < 1)
     return BODE_ERR_BAD_ARG;
   if (form != BODE_FORM_REFERENCE && form != BODE_FORM_LOG1P) return BODE_ERR_BAD_ARG;
@@ -147,7 +204,7 @@ static int score_common(const void* workspace, int n, int d, int S, const double
   const Layout L = make_layout(n, d, S);
   if (plan_score(L, Nd, props.sm_count, props.smem_optin, &P) != 0) return BODE_ERR_UNSUPPORTED;
   ScoreArgs a;
-  a.ws = workspace; a.L = L; a.Xd = Xd; a.Nd = Nd; a.logk = logk; a.S = S;
+  a.ws = workspace; a.L = L; a.Xd = Xd; a.Nd = Nd; a.logk = logk; a.S = S; a.xi_ovr = xi_ovr;
   a.sc = P.sc; a.ntiles = P.ntiles; a.form = form; a.mode = mode;
   {
     const char* dbg = getenv("BODE_DEBUG_SKIP");
@@ -181,7 +238,7 @@ static int score_common(const void* workspace, int n, int d, int S, const double
 int bode_ekld_score_dev(const void* workspace, int n, int d, int S, const double* X_design, int64_t Nd,
                         int64_t idx_offset, int form, double* logk, double* score, double* var, double* best,
                         int64_t* best_idx, void* scratch, void* stream) {
-  return score_common(workspace, n, d, S, X_design, Nd, idx_offset, form, kModeEkld, logk, score, var, best, best_idx,
+  return score_common(workspace, n, d, S, X_design, Nd, idx_offset, form, kModeEkld, nullptr, logk, score, var, best, best_idx,
                       scratch, stream, nullptr);
 }
 
@@ -189,14 +246,25 @@ int bode_ekld_score_dev_timed(const void* workspace, int n, int d, int S, const 
                               int64_t idx_offset, int form, double* logk, double* score, double* var, double* best,
                               int64_t* best_idx, void* scratch, void* stream, float* score_kernel_ms) {
   if (!score_kernel_ms) return BODE_ERR_BAD_ARG;
-  return score_common(workspace, n, d, S, X_design, Nd, idx_offset, form, kModeEkld, logk, score, var, best, best_idx,
+  return score_common(workspace, n, d, S, X_design, Nd, idx_offset, form, kModeEkld, nullptr, logk, score, var, best, best_idx,
                       scratch, stream, score_kernel_ms);
+}
+
+int bode_ekld_score_quad_dev(const void* workspace, int n, int d, int S, const double* hyp, int ndim,
+                             const double* X_design, int64_t Nd, int64_t idx_offset, int form, const double* Xq,
+                             const double* wq, int Nq, double* xi /* S*Nd scratch */, double* logk, double* score,
+                             double* var, double* best, int64_t* best_idx, void* scratch, void* stream) {
+  if (!hyp || !Xq || !xi || Nq < 1) return BODE_ERR_BAD_ARG;
+  int rc = bode_quad_rowmean_dev(hyp, S, ndim, d, X_design, Nd, Xq, wq, Nq, xi, scratch, stream);  // xi_q(x) for every (s, x)
+  if (rc != BODE_OK) return rc;
+  return score_common(workspace, n, d, S, X_design, Nd, idx_offset, form, kModeEkld, xi, logk, score, var, best, best_idx,
+                      static_cast<char*>(scratch) + 256, stream, nullptr);
 }
 
 int bode_us_variance_dev(const void* workspace, int n, int d, int S, const double* X_grid, int64_t Ng,
                          int64_t idx_offset, double* sigx, double* pred_var, double* best, int64_t* best_idx,
                          void* scratch, void* stream) {
-  return score_common(workspace, n, d, S, X_grid, Ng, idx_offset, BODE_FORM_REFERENCE, kModeVariance, sigx, pred_var,
+  return score_common(workspace, n, d, S, X_grid, Ng, idx_offset, BODE_FORM_REFERENCE, kModeVariance, nullptr, sigx, pred_var,
                       nullptr, best, best_idx, scratch, stream, nullptr);
 }
 

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
         const double x = a.X[(size_t)j * d + k];
         p *= (SQRTPI / SQRT2) * h[1 + k] * (erf((1.0 - x) * ck[k]) - erf((0.0 - x) * ck[k]));
       }
-      e = ss * p;
+      e = a.e_ovr ? a.e_ovr[(size_t)s * n + j] : ss * p;
       y = a.Y[j];
     }
     Lw[(size_t)n * npad + j] = e;
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
       const double ell = h[1 + k], zk = 1.0 / (SQRT2 * ell);
       p *= 2.0 * SQRTPI * (ell * ell) * (zk * erf(zk) + exp(-(zk * zk)) / SQRTPI - 1.0 / SQRTPI);
     }
-    const double sigma0 = ss * p;
+    const double sigma0 = a.sigma0_ovr ? a.sigma0_ovr[s] : ss * p;
     cst[C_SS] = ss; cst[C_NOISE] = noise; cst[C_SIGMA0] = sigma0; cst[C_SIGMA1] = sigma0 - saa; cst[C_MU1] = sza;
     cst[C_LOGDET] = sld; cst[C_QUAD] = szz;
     cst[C_LOGLIK] = 0.5 * (-(double)n * 1.8378770664093453 - sld - szz);  // log(2 pi)

@@ -12,5 +12,8 @@ struct PrepArgs {
   char* ws;
   Layout L;
   int* info;  // S
+  // quadrature mode (nullable): kernel mean embedding of the observations and double integral supplied by k_rowmean
+  const double* e_ovr;       // S*n   replaces xik(X)
+  const double* sigma0_ovr;  // S     replaces bk
 };
 }  // namespace bode

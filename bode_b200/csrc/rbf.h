@@ -31,4 +31,28 @@ __device__ __forceinline__ double rbf_exp(double x, const double* __restrict__ t
   return __hiloint2double(__double2hiint(res) + (e << 20), __double2loint(res));
 }
 
+// sum_k (u[k] - y[k])^2 over DP dimensions, u in shared/global memory (16-byte aligned rows), y in registers
+template <int DP>
+__device__ __forceinline__ double sqdist(const double* __restrict__ uj, const double (&y)[DP]) {
+  double r2;
+  if (DP == 1) {
+    const double t = uj[0] - y[0];
+    r2 = t * t;
+  } else {
+    r2 = 0.0;
+#pragma unroll
+    for (int k2 = 0; k2 < DP / 2; k2++) {
+      const double2 u = *reinterpret_cast<const double2*>(uj + 2 * k2);
+      const double t0 = u.x - y[2 * k2], t1 = u.y - y[2 * k2 + 1];
+      r2 = fma(t0, t0, r2);
+      r2 = fma(t1, t1, r2);
+    }
+    if (DP & 1) {
+      const double t = uj[DP - 1] - y[DP - 1];
+      r2 = fma(t, t, r2);
+    }
+  }
+  return r2;
+}
+
 }  // namespace bode

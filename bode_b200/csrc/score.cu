@@ -93,29 +93,6 @@ __device__ __forceinline__ bool elect_one() {
 // ----------------------------------------------------------------------------------------------------------------
 // Phase A: Kc[(g*C + c)*4 + kk] = ss * exp(-sum_k (U[4g+kk][k] - x_c[k] ck[k])^2); partial w.k; partial xik factors
 // ----------------------------------------------------------------------------------------------------------------
-template <int DP>
-__device__ __forceinline__ double sqdist(const double* __restrict__ uj, const double (&y)[DP]) {
-  double r2;
-  if (DP == 1) {
-    const double t = uj[0] - y[0];
-    r2 = t * t;
-  } else {
-    r2 = 0.0;
-#pragma unroll
-    for (int k2 = 0; k2 < DP / 2; k2++) {
-      const double2 u = *reinterpret_cast<const double2*>(uj + 2 * k2);
-      const double t0 = u.x - y[2 * k2], t1 = u.y - y[2 * k2 + 1];
-      r2 = fma(t0, t0, r2);
-      r2 = fma(t1, t1, r2);
-    }
-    if (DP & 1) {
-      const double t = uj[DP - 1] - y[DP - 1];
-      r2 = fma(t, t, r2);
-    }
-  }
-  return r2;
-}
-
 template <int DP, int C, int NT>
 __device__ __forceinline__ void phase_a(const double* __restrict__ aux, const double* __restrict__ U, int dpad, int g_lo, int g_hi, int d,
                                         const double* __restrict__ xt, double* __restrict__ Kc,
@@ -454,7 +431,7 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && CT <= 2) ? 2 : 
       double wk = 0.0, xf = 1.0;
 #pragma unroll
       for (int j = 0; j < NJQ; j++) { wk += pvp[j * C + tid]; xf *= xipp[j * C + tid]; }
-      const double xi = ss * xf;
+      const double xi = a.xi_ovr ? ((c0 + tid < a.Nd) ? a.xi_ovr[(size_t)(s_begin + ls) * a.Nd + c0 + tid] : 0.0) : ss * xf;
       const double sigma_x = ss - tt;  // latent predictive variance (GPy predict, full_cov 1x1)
       double outv;
       if (a.mode == kModeVariance) {

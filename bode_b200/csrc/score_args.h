@@ -25,6 +25,7 @@ struct ScoreArgs {
   const double* Xd;  // Nd * d
   int64_t Nd;
   double* logk;      // S * Nd
+  const double* xi_ovr;  // S * Nd or null: quadrature estimate of xik(x) (k_rowmean); null = closed form (erf)
   int S;
   int sc;            // hyper-samples per work item
   int ntiles;        // candidate tiles

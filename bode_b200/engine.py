@@ -35,6 +35,8 @@ class EkldEngine:
         self.info = None
         self._scratch = {}
         self.last_kernel_ms = None
+        self.quad = None
+        self._ndim = 0
 
     # ---- helpers -------------------------------------------------------------------------------------------
     def _dev(self, a, shape=None):
@@ -57,8 +59,11 @@ class EkldEngine:
         return t
 
     # ---- K1 ------------------------------------------------------------------------------------------------
-    def prepare(self, X, Y, hyp, nugget_var, jitter=GPY_JITTER):
-        """Factorise every hyper-sample (``bode_ekld_prepare_dev``).  hyp: (S, d+1) or (S, d+2) reference layout."""
+    def prepare(self, X, Y, hyp, nugget_var, jitter=GPY_JITTER, quad=None):
+        """Factorise every hyper-sample (``bode_ekld_prepare_dev``).  hyp: (S, d+1) or (S, d+2) reference layout.
+
+        quad=(X_quad, weights|None) switches to quadrature mode: the kernel integrals xik / bk are replaced by
+        (weighted) means over the quadrature points, here and in the following ``score`` calls."""
         with torch.cuda.device(self.device):
             Xd = self._dev(X)
             n, d = Xd.shape
@@ -75,10 +80,28 @@ class EkldEngine:
             if self.ws is None or self.ws.numel() < nbytes:
                 self.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             self.info = self._buf("info", S, torch.int32)[:S]
-            _ext.check(self.lib.bode_ekld_prepare_dev(_ptr(Xd), _ptr(Yd), _ptr(H), n, d, S, ndim, float(nugget_var),
-                                                      float(jitter), _ptr(self.ws), self.ws.numel(), _ptr(self.info),
-                                                      self._stream()))
+            self.quad = None
+            if quad is None:
+                _ext.check(self.lib.bode_ekld_prepare_dev(_ptr(Xd), _ptr(Yd), _ptr(H), n, d, S, ndim, float(nugget_var),
+                                                          float(jitter), _ptr(self.ws), self.ws.numel(), _ptr(self.info),
+                                                          self._stream()))
+            else:
+                Xq = self._dev(quad[0])
+                if Xq.dim() == 1:
+                    Xq = Xq.reshape(-1, 1)
+                if Xq.shape[1] != d:
+                    raise ValueError("quadrature points have %d columns, observations have %d" % (Xq.shape[1], d))
+                wq = None if quad[1] is None else self._dev(quad[1]).reshape(-1)
+                if wq is not None and wq.numel() != Xq.shape[0]:
+                    raise ValueError("one weight per quadrature point")
+                Nq = Xq.shape[0]
+                qs = self._buf("quad_scratch", self.lib.bode_quad_scratch_bytes(n, S, Nq), torch.uint8)
+                _ext.check(self.lib.bode_ekld_prepare_quad_dev(_ptr(Xd), _ptr(Yd), _ptr(H), n, d, S, ndim, float(nugget_var),
+                                                               float(jitter), _ptr(Xq), _ptr(wq), Nq, _ptr(self.ws),
+                                                               self.ws.numel(), _ptr(self.info), _ptr(qs), self._stream()))
+                self.quad = (Xq, wq, Nq)
             self.n, self.d, self.S = n, d, S
+            self._ndim = ndim
             self._keep = (Xd, Yd, H)  # keep inputs alive until the stream has consumed them
         return self.info
 
@@ -115,9 +138,18 @@ class EkldEngine:
             var = torch.empty(Nd, dtype=torch.float64, device=self.device) if want_var else None
             best = torch.empty(1, dtype=torch.float64, device=self.device)
             best_idx = torch.empty(1, dtype=torch.int64, device=self.device)
-            scr = self._buf("scratch", self.lib.bode_ekld_score_scratch_bytes(Nd), torch.uint8)
+            scr = self._buf("scratch", 256 + self.lib.bode_ekld_score_scratch_bytes(Nd), torch.uint8)
             args = [_ptr(self.ws), self.n, self.d, self.S, _ptr(Xd), Nd, int(idx_offset), int(form), _ptr(logk),
                     _ptr(score), _ptr(var), _ptr(best), _ptr(best_idx), _ptr(scr), self._stream()]
+            if self.quad is not None:
+                Xq, wq, Nq = self.quad
+                xi = self._buf("xi", self.S * Nd, torch.float64)[: self.S * Nd].view(self.S, Nd)
+                _ext.check(self.lib.bode_ekld_score_quad_dev(_ptr(self.ws), self.n, self.d, self.S, _ptr(self._keep[2]),
+                                                             self._ndim, _ptr(Xd), Nd, int(idx_offset), int(form), _ptr(Xq),
+                                                             _ptr(wq), Nq, _ptr(xi), _ptr(logk), _ptr(score), _ptr(var),
+                                                             _ptr(best), _ptr(best_idx), _ptr(scr), self._stream()))
+                self._keep_x = Xd
+                return dict(score=score, var=var, logk=logk, best=best, best_idx=best_idx, xi=xi)
             if timed:
                 ms = ctypes.c_float(0.0)
                 _ext.check(self.lib.bode_ekld_score_dev_timed(*args, ctypes.c_void_p(ctypes.addressof(ms))))
@@ -149,14 +181,14 @@ class EkldEngine:
 
 
 def ekld_score(X, Y, hyp, X_design, nugget=1e-3, jitter=GPY_JITTER, form=_ext.BODE_FORM_REFERENCE, engine=None,
-               want_kld=False):
+               want_kld=False, quad=None):
     """One-call public API with host (NumPy) buffers: prepare + score + summary, results back on the host.
 
     Returns dict(score, var, argmax, best, mu_Q, sigma_Q, info[, kld]).  This is the dense generalisation of
     ``KLSampler.mcmc_kld`` (``_sampler.py:483-492``) over all rows of ``X_design``.
     """
     eng = EkldEngine() if engine is None else engine
-    info = eng.prepare(X, Y, hyp, nugget ** 2, jitter)
+    info = eng.prepare(X, Y, hyp, nugget ** 2, jitter, quad=quad)
     r = eng.score(X_design, form=form)
     mu, sg = eng.mu_sigma()
     out = dict(score=r["score"].cpu().numpy(), var=r["var"].cpu().numpy(), argmax=int(r["best_idx"].item()),

@@ -94,6 +94,28 @@ int bode_ekld_score_dev_timed(const void* workspace, int n, int d, int S, const 
                               int64_t idx_offset, int form, double* logk, double* score, double* var, double* best,
                               int64_t* best_idx, void* scratch, void* stream, float* score_kernel_ms);
 
+/* ---- quadrature mode (north star: k(X_design, X_quad) / k(X, X_quad) averaged over quadrature points) ------------------
+ * The reference integrates the kernel over [0,1]^d in closed form (xik / bk, `_core.py:86-101`); quadrature mode
+ * replaces the three integrals by (weighted) means over user-supplied quadrature points X_quad[Nq*d] (the drivers'
+ * `quad_points`, `samp_ex1.py:61-62`; `wq` nullable = uniform weights):
+ *     e_q[j] = mean_q k(X_j, x_q),   xi_q(x) = mean_q k(x, x_q),   sigma0_q = mean_{q,q'} k(x_q, x_q').
+ * It differs from the reference by quadrature error (SURVEY note Q) and is parity-checked against the oracle's own
+ * quadrature variant on the same X_quad. */
+size_t bode_quad_scratch_bytes(int n, int S, int Nq);
+/* out[s*Np + i] = (variance_s / sum w) * sum_q w_q exp(-|| (P_i - x_q) / (sqrt2 ell_s) ||^2); scratch >= 256 bytes. */
+int bode_quad_rowmean_dev(const double* hyp, int S, int ndim, int d, const double* P, int64_t Np, const double* Xq,
+                          const double* wq, int Nq, double* out, void* scratch, void* stream);
+/* bode_ekld_prepare_dev with e_q and sigma0_q in place of xik(X) and bk; scratch >= bode_quad_scratch_bytes(n,S,Nq). */
+int bode_ekld_prepare_quad_dev(const double* X, const double* Y, const double* hyp, int n, int d, int S, int ndim,
+                               double nugget_var, double jitter, const double* Xq, const double* wq, int Nq,
+                               void* workspace, size_t workspace_bytes, int* info, void* scratch, void* stream);
+/* bode_ekld_score_dev with xi_q(x) in place of xik(x); xi is an S*Nd scratch (returned filled);
+ * scratch >= 256 + bode_ekld_score_scratch_bytes(Nd). */
+int bode_ekld_score_quad_dev(const void* workspace, int n, int d, int S, const double* hyp, int ndim,
+                             const double* X_design, int64_t Nd, int64_t idx_offset, int form, const double* Xq,
+                             const double* wq, int Nq, double* xi, double* logk, double* score, double* var, double* best,
+                             int64_t* best_idx, void* scratch, void* stream);
+
 /* Uncertainty-sampling comparator (`update_comp_models`, `_sampler.py:506-514`): pred_var[c] = mean_s latent
  * predictive variance at X_grid[c]; best/best_idx as above. Reuses the scoring kernel (no v / EKLD epilogue). */
 int bode_us_variance_dev(const void* workspace, int n, int d, int S, const double* X_grid, int64_t Ng,

@@ -49,9 +49,21 @@ static ld rbf_ld(const double *a, const double *b, const ld *ell, ld ss, int d) 
  * hyp: (S, ndim) rows [variance, ell_1..ell_d (, noise_std)]; noise variance = hyp[-1]^2 if ndim==d+2 else nugget_var.
  * Outputs (double, any may be NULL): kld (S*Nd), sigx (S*Nd, latent predictive variance), v (S*Nd),
  * mu1 (S), sig1 (S), loglik (S). */
+/* (weighted) mean over the quadrature points of k(x, x_q): quadrature stand-in for xik (north-star quad mode) */
+static ld quad_mean_ld(const double *x, const double *Xq, const double *wq, long Nq, const ld *ell, ld ss, int d) {
+    ld acc = 0.0L, wsum = 0.0L;
+    for (long q = 0; q < Nq; q++) {
+        ld w = wq ? (ld)wq[q] : 1.0L;
+        acc += w * rbf_ld(x, Xq + (size_t)q * d, ell, ss, d);
+        wsum += w;
+    }
+    return acc / wsum;
+}
+
 int ekld_truth(const double *X, const double *Y, int n, int d, const double *hyp, int S, int ndim,
                double nugget_var, double jitter, const double *Xd, long Nd,
-               double *kld, double *sigx, double *v_out, double *mu1, double *sig1, double *loglik) {
+               double *kld, double *sigx, double *v_out, double *mu1, double *sig1, double *loglik,
+               const double *Xq, const double *wq, long Nq) {
     ld *A = (ld *)malloc(sizeof(ld) * (size_t)n * n);
     ld *e = (ld *)malloc(sizeof(ld) * n), *a = (ld *)malloc(sizeof(ld) * n), *w = (ld *)malloc(sizeof(ld) * n);
     ld *al = (ld *)malloc(sizeof(ld) * n), *k = (ld *)malloc(sizeof(ld) * n), *ell = (ld *)malloc(sizeof(ld) * d);
@@ -81,7 +93,8 @@ int ekld_truth(const double *X, const double *Y, int n, int d, const double *hyp
             }
         }
         if (rc) break;
-        for (int i = 0; i < n; i++) e[i] = xik_ld(X + (size_t)i * d, ell, ss, d);
+        for (int i = 0; i < n; i++)
+            e[i] = Xq ? quad_mean_ld(X + (size_t)i * d, Xq, wq, Nq, ell, ss, d) : xik_ld(X + (size_t)i * d, ell, ss, d);
         /* a = L^-1 e ; w = L^-T a ; al = A^-1 Y */
         for (int i = 0; i < n; i++) {
             ld t = e[i];
@@ -105,14 +118,25 @@ int ekld_truth(const double *X, const double *Y, int n, int d, const double *hyp
             for (int q = i + 1; q < n; q++) t -= A[(size_t)q * n + i] * al[q];
             al[i] = t / A[(size_t)i * n + i];
         }
-        ld s1 = bk_ld(ell, ss, d), m1 = 0.0L;
+        ld s1, m1 = 0.0L;
+        if (Xq) {
+            ld acc = 0.0L, wsum = 0.0L;
+            for (long q = 0; q < Nq; q++) {
+                ld w = wq ? (ld)wq[q] : 1.0L;
+                acc += w * quad_mean_ld(Xq + (size_t)q * d, Xq, wq, Nq, ell, ss, d);
+                wsum += w;
+            }
+            s1 = acc / wsum;
+        } else {
+            s1 = bk_ld(ell, ss, d);
+        }
         for (int i = 0; i < n; i++) { s1 -= a[i] * a[i]; m1 += al[i] * e[i]; }
         if (mu1) mu1[s] = (double)m1;
         if (sig1) sig1[s] = (double)s1;
         if (loglik) loglik[s] = (double)(0.5L * (-(ld)n * logl(2.0L * acosl(-1.0L)) - logdet - quad));
         for (long c = 0; c < Nd; c++) {
             const double *x = Xd + (size_t)c * d;
-            ld vv = xik_ld(x, ell, ss, d), tt = 0.0L;
+            ld vv = Xq ? quad_mean_ld(x, Xq, wq, Nq, ell, ss, d) : xik_ld(x, ell, ss, d), tt = 0.0L;
             for (int i = 0; i < n; i++) { k[i] = rbf_ld(X + (size_t)i * d, x, ell, ss, d); vv -= w[i] * k[i]; }
             for (int i = 0; i < n; i++) {
                 ld t = k[i];

@@ -27,7 +27,7 @@ def _load():
         _lib.ekld_truth.restype = ctypes.c_int
         _lib.ekld_truth.argtypes = [dp, dp, ctypes.c_int, ctypes.c_int, dp, ctypes.c_int, ctypes.c_int,
                                     ctypes.c_double, ctypes.c_double, dp, ctypes.c_long,
-                                    dp, dp, dp, dp, dp, dp]
+                                    dp, dp, dp, dp, dp, dp, dp, dp, ctypes.c_long]
     return _lib
 
 
@@ -35,7 +35,7 @@ def _p(a):
     return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
 
 
-def ekld_truth(X, Y, X_design, hyp, nugget=1e-3, jitter=1e-8):
+def ekld_truth(X, Y, X_design, hyp, nugget=1e-3, jitter=1e-8, quad=None):
     """dict(kld (S,Nd), sigma_x (S,Nd), v (S,Nd), mu_1 (S), sigma_1 (S), loglik (S)) rounded from long double."""
     lib = _load()
     X = np.ascontiguousarray(X, dtype=np.float64)
@@ -47,8 +47,15 @@ def ekld_truth(X, Y, X_design, hyp, nugget=1e-3, jitter=1e-8):
     Nd = Xd.shape[0]
     kld = np.empty((S, Nd)); sx = np.empty((S, Nd)); v = np.empty((S, Nd))
     mu1 = np.empty(S); s1 = np.empty(S); ll = np.empty(S)
+    Xq = wq = None
+    Nq = 0
+    if quad is not None:
+        Xq = np.ascontiguousarray(np.atleast_2d(quad[0]), dtype=np.float64)
+        Nq = Xq.shape[0]
+        wq = None if quad[1] is None else np.ascontiguousarray(quad[1], dtype=np.float64)
     rc = lib.ekld_truth(_p(X), _p(Y), n, d, _p(hyp), S, ndim, float(nugget) ** 2, float(jitter), _p(Xd), Nd,
-                        _p(kld), _p(sx), _p(v), _p(mu1), _p(s1), _p(ll))
+                        _p(kld), _p(sx), _p(v), _p(mu1), _p(s1), _p(ll),
+                        _p(Xq) if Xq is not None else None, _p(wq) if wq is not None else None, Nq)
     if rc != 0:
         raise np.linalg.LinAlgError("long-double Cholesky failed at sample %d" % (rc - 1))
     return dict(kld=kld, sigma_x=sx, v=v, mu_1=mu1, sigma_1=s1, loglik=ll)

@@ -304,3 +304,41 @@ def test_example_driver_outputs(tmp_path):
     assert models[0][0].shape == (60, 2) and models[0][0].dtype == np.float64 and (models[0][0] > 0).all()
     # the true mean of Ex1Func is -1.35...: three points already pin it loosely; the estimate must be in the ballpark
     assert -2.0 < mu[-1] < -0.8
+
+
+# ---- quadrature mode (north star: k(X_design, X_quad), k(X, X_quad) averaged over quadrature points) --------------------
+@pytest.mark.parametrize("weighted", [False, True])
+def test_quad_mode_parity(engine, weighted):
+    """Kernel integrals replaced by means over X_quad; no reference call site exists (the reference integrates in closed
+    form), so parity is against the oracle's quadrature variant and the long-double truth on the same X_quad."""
+    X, Y, Xd, hyp = cases.make_problem(3, 24, 5, 300, seed=61, ell_lo=0.1, ell_hi=0.3)
+    rng = np.random.default_rng(8)
+    Xq = rng.random((700, 3))
+    wq = (rng.random(700) + 0.5) if weighted else None
+    engine.prepare(X, Y, hyp, 1e-6, quad=(Xq, wq))
+    r = engine.score(Xd)
+    got = np.exp(r["logk"].cpu().numpy())
+    ref = orc.score(X, Y, Xd, hyp, quad=(Xq, wq))
+    t = truth.ekld_truth(X, Y, Xd, hyp, quad=(Xq, wq))
+    assert_parity(got, ref["kld"], t["kld"], min_trusted=0.6)
+    assert_argmax(int(r["best_idx"].item()), ref["score"])
+    mu, sg = engine.mu_sigma()
+    assert abs(mu - ref["mu_Q"]) <= 1e-10 * abs(ref["mu_Q"]) + 1e-13 and abs(sg - ref["sigma_Q"]) <= 1e-8 * abs(ref["sigma_Q"])
+    # xi_q(x) itself
+    m0 = orc.make_mcmc_model(hyp[0], X, Y)
+    np.testing.assert_allclose(r["xi"][0].cpu().numpy(), orc.quad_mean(m0, Xd, Xq, wq), rtol=1e-12)
+
+
+def test_quad_mode_converges_to_closed_form(engine):
+    """With a fine midpoint rule in 1-D the quadrature mode reproduces the reference's closed-form mode."""
+    X, Y, Xd, hyp = cases.make_problem(1, 6, 4, 200, seed=5, ell_lo=0.15, ell_hi=0.4)
+    Xq = ((np.arange(20000) + 0.5) / 20000)[:, None]
+    engine.prepare(X, Y, hyp, 1e-6)
+    closed = engine.score(Xd)["score"].cpu().numpy()
+    mu_c, sg_c = engine.mu_sigma()
+    engine.prepare(X, Y, hyp, 1e-6, quad=(Xq, None))
+    quad = engine.score(Xd)["score"].cpu().numpy()
+    mu_q, sg_q = engine.mu_sigma()
+    assert abs(mu_q - mu_c) < 1e-6 * abs(mu_c) and abs(sg_q - sg_c) < 1e-4 * abs(sg_c)
+    keep = closed > np.median(closed)  # away from the zeros of v, where log EKLD is steep
+    np.testing.assert_allclose(quad[keep], closed[keep], atol=2e-3)

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libbode_b200.so")
+LIB_PATH = os.environ.get("BODE_B200_LIB", os.path.join(_HERE, "lib", "libbode_b200.so"))  # env override: developer builds
 
 BODE_FORM_REFERENCE = 0
 BODE_FORM_LOG1P = 1

@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && CT <= 2) ? 2 : 
   // so that the epilogue hides under the other slices' phase A instead of delaying the post-A barrier.
   int ga_lo, ga_hi;
   {
-    constexpr int kEpiGroups = 3;
+    const int kEpiGroups = a.epi_groups;
     const int jq = tid / C;
     const int n0 = (ng >= 4 * NJQ) ? max(0, ng / NJQ - kEpiGroups) : ng / NJQ;
     const int rest = ng - n0, per = (NJQ > 1) ? rest / (NJQ - 1) : 0, extra = (NJQ > 1) ? rest - per * (NJQ - 1) : 0;
@@ -575,6 +575,7 @@ static int plan_variant(const Layout& L, size_t smem_limit, ScorePlan* P) {
   // packed up to the chunk size
   const size_t pair0_doubles = (size_t)nrt * 64;
   size_t chunk_max = 2048;  // 16 KB
+  if (const char* ck = getenv("BODE_CHUNK_KB")) chunk_max = (size_t)atoi(ck) * 128;  // tuning knob
   if (chunk_max < pair0_doubles) chunk_max = pair0_doubles;
   int nch = 0;
   int g = 0;
@@ -637,7 +638,9 @@ int plan_score(const Layout& L, int64_t Nd, int sm_count, size_t smem_optin, Sco
   // work items: (tile, sample chunk); aim for >= 16 waves of CTAs, keep at least 4 samples per item when possible
   const int64_t ntiles = (Nd + C - 1) / C;
   int sc = L.S;
-  const int64_t target = (int64_t)16 * sm_count;
+  int waves = 16;
+  if (const char* wv = getenv("BODE_WAVES")) waves = atoi(wv);  // tuning knob
+  const int64_t target = (int64_t)waves * sm_count;
   while (sc > 4 && ntiles * ((L.S + sc - 1) / sc) < target) sc = (sc + 1) / 2;
   if (ntiles * ((L.S + sc - 1) / sc) < sm_count) {
     while (sc > 1 && ntiles * ((L.S + sc - 1) / sc) < sm_count) sc = (sc + 1) / 2;

@@ -32,6 +32,7 @@ struct ScoreArgs {
   int form, mode;
   int debug_skip;    // developer timing knob (env BODE_DEBUG_SKIP): 1 = skip phase A after the first sample, 2 = skip phase B's DMMAs
   int stages, chunk_max /* doubles */, nchunks;
+  int epi_groups;    // phase-A groups the epilogue slice (threads < C) is relieved of (tuning knob, default 3)
   int u_global;      // 1: the prescaled observations U stay in global memory (large n: they do not fit in smem)
   unsigned short chunk_g0[kMaxChunks + 1];
   short tile_id[kMaxRG * kMaxRT];  // [rg][slot], right-aligned ascending, -1 = unused

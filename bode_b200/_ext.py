@@ -22,7 +22,7 @@ EXPORTS = (
     "bode_version", "bode_strerror", "bode_last_cuda_error", "bode_ekld_workspace_bytes", "bode_ekld_prepare_dev",
     "bode_ekld_sample_terms_dev", "bode_ekld_mu_sigma_dev", "bode_ekld_score_scratch_bytes", "bode_ekld_score_dev",
     "bode_ekld_score_dev_timed", "bode_us_variance_dev", "bode_quad_scratch_bytes", "bode_quad_rowmean_dev",
-    "bode_ekld_prepare_quad_dev", "bode_ekld_score_quad_dev", "bode_ekld_score_host", "bode_gp_loglik_host", "bode_fp64_peak",
+    "bode_ekld_prepare_quad_dev", "bode_ekld_score_quad_dev", "bode_ekld_score_host", "bode_gp_loglik_host", "bode_gp_loglik_dev", "bode_fp64_peak",
 )
 
 
@@ -91,6 +91,9 @@ def load():
     lib.bode_gp_loglik_host.restype = ctypes.c_int
     lib.bode_gp_loglik_host.argtypes = [c_dp, c_dp, c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_double, ctypes.c_double, c_dp]
+    lib.bode_gp_loglik_dev.restype = ctypes.c_int
+    lib.bode_gp_loglik_dev.argtypes = [c_dp, c_dp, c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_double, ctypes.c_double, c_dp, ctypes.c_size_t, c_dp, c_dp, c_dp]
     lib.bode_fp64_peak.restype = ctypes.c_int
     lib.bode_fp64_peak.argtypes = [c_dp, c_dp]
     _lib = lib

@@ -172,9 +172,7 @@ class KLSampler(object):
         return float(self._loglik_batch(np.atleast_2d(param), X, Y)[0])
 
     def _loglik_batch(self, params, X, Y):
-        eng = self.engine
-        eng.prepare(X, Y, params, self.nugget ** 2)
-        return eng.sample_terms()[:, 7].cpu().numpy()
+        return self.engine.loglik(X, Y, params, self.nugget ** 2)
 
     def lnprob(self, param, model, X, Y):
         """Log posterior of one row, or of a (k, ndim) block of rows (vectorised stand-in path)."""
@@ -186,8 +184,14 @@ class KLSampler(object):
         out = np.full(param.shape[0], -np.inf)
         ok = ~np.any(param <= 0, axis=1)
         if np.any(ok):
-            ll = self._loglik_batch(param[ok], X, Y)
-            pr = np.array([self.get_log_prior(p) for p in param[ok]], dtype=np.float64)
+            good = param[ok]
+            ll = self._loglik_batch(good, X, Y)
+            d = self.X.shape[1]
+            pr = np.asarray(self.variance_prior(good[:, 0]), dtype=np.float64) * np.ones(good.shape[0])
+            for j in range(d):
+                pr = pr + self.lengthscale_prior(good[:, j + 1])
+            if self.noisy:
+                pr = pr + self.noise_prior(good[:, -1])
             out[ok] = ll + pr
         out[np.isnan(out)] = -np.inf
         return out

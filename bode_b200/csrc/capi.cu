@@ -18,6 +18,7 @@ namespace bode {
 cudaError_t launch_prepare(const PrepArgs& a, cudaStream_t st);
 cudaError_t launch_sample_terms(const void* ws, const Layout& L, double* out, cudaStream_t st);
 cudaError_t launch_mu_sigma(const void* ws, const Layout& L, double* out, cudaStream_t st);
+cudaError_t launch_loglik_gather(const void* ws, const Layout& L, double* out, cudaStream_t st);
 int plan_score(const Layout& L, int64_t Nd, int sm_count, size_t smem_optin, ScorePlan* P);
 cudaError_t launch_score(const ScoreArgs& a, const ScorePlan& P, cudaStream_t st);
 cudaError_t launch_reduce(const double* logk, int S, int64_t Nd, int64_t idx_offset, double* score, double* var,
@@ -115,6 +116,7 @@ int bode_ekld_prepare_dev(const double* X, const double* Y, const double* hyp, i
   a.info = info;
   a.e_ovr = nullptr;
   a.sigma0_ovr = nullptr;
+  a.loglik_only = 0;
   if (workspace_bytes < a.L.total_bytes || (reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return BODE_ERR_WORKSPACE;
   BODE_CUDA(launch_prepare(a, static_cast<cudaStream_t>(stream)));
   return BODE_OK;
@@ -165,8 +167,31 @@ int bode_ekld_prepare_quad_dev(const double* X, const double* Y, const double* h
   a.info = info;
   a.e_ovr = e;
   a.sigma0_ovr = s0;
+  a.loglik_only = 0;
   if (workspace_bytes < a.L.total_bytes || (reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return BODE_ERR_WORKSPACE;
   BODE_CUDA(launch_prepare(a, st));
+  return BODE_OK;
+}
+
+int bode_gp_loglik_dev(const double* X, const double* Y, const double* hyp, int n, int d, int S, int ndim,
+                       double nugget_var, double jitter, void* workspace, size_t workspace_bytes, int* info, double* loglik,
+                       void* stream) {
+  if (!X || !Y || !hyp || !workspace || !info || !loglik || !shape_ok(n, d, S)) return BODE_ERR_BAD_ARG;
+  if (ndim != d + 1 && ndim != d + 2) return BODE_ERR_BAD_ARG;
+  if (!shape_supported(n, d)) return BODE_ERR_UNSUPPORTED;
+  PrepArgs a;
+  a.X = X; a.Y = Y; a.hyp = hyp; a.n = n; a.d = d; a.S = S; a.ndim = ndim;
+  a.nugget_var = nugget_var; a.jitter = jitter;
+  a.ws = static_cast<char*>(workspace);
+  a.L = make_layout(n, d, S);
+  a.info = info;
+  a.e_ovr = nullptr;
+  a.sigma0_ovr = nullptr;
+  a.loglik_only = 1;
+  if (workspace_bytes < a.L.total_bytes || (reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return BODE_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BODE_CUDA(launch_prepare(a, st));
+  BODE_CUDA(launch_loglik_gather(workspace, a.L, loglik, st));
   return BODE_OK;
 }
 
@@ -340,14 +365,10 @@ int bode_gp_loglik_host(const double* X, const double* Y, const double* hyp, int
   BODE_CUDA(cudaMemcpy(dX.p, X, sizeof(double) * n * d, cudaMemcpyHostToDevice));
   BODE_CUDA(cudaMemcpy(dY.p, Y, sizeof(double) * n, cudaMemcpyHostToDevice));
   BODE_CUDA(cudaMemcpy(dH.p, hyp, sizeof(double) * S * ndim, cudaMemcpyHostToDevice));
-  int rc = bode_ekld_prepare_dev(dX.as<double>(), dY.as<double>(), dH.as<double>(), n, d, S, ndim, nugget_var, jitter,
-                                 dWs.p, wsb, dInfo.as<int>(), nullptr);
+  int rc = bode_gp_loglik_dev(dX.as<double>(), dY.as<double>(), dH.as<double>(), n, d, S, ndim, nugget_var, jitter, dWs.p, wsb,
+                              dInfo.as<int>(), dT.as<double>(), nullptr);
   if (rc != BODE_OK) return rc;
-  rc = bode_ekld_sample_terms_dev(dWs.p, n, d, S, dT.as<double>(), nullptr);
-  if (rc != BODE_OK) return rc;
-  std::vector<double> t((size_t)S * kConsts);
-  BODE_CUDA(cudaMemcpy(t.data(), dT.p, sizeof(double) * S * kConsts, cudaMemcpyDeviceToHost));
-  for (int s = 0; s < S; s++) loglik[s] = t[(size_t)s * kConsts + C_LOGLIK];
+  BODE_CUDA(cudaMemcpy(loglik, dT.p, sizeof(double) * S, cudaMemcpyDeviceToHost));
   return BODE_OK;
 }
 

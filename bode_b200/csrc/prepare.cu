@@ -294,6 +294,8 @@ __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
     a.info[s] = 0;
   }
 
+  if (a.loglik_only) return;  // the MCMC likelihood path needs only consts[C_LOGLIK]
+
   // ---- w = L^-T a : blocked back-substitution, 8 unknowns per step ---------------------------------------------
   for (int j = tid; j < npad; j += kPrepThreads) vec[j] = (j < n) ? arow[j] : 0.0;
   __syncthreads();
@@ -401,6 +403,17 @@ __global__ void k_mu_sigma(const char* ws, Layout L, double* out) {
   }
   out[0] = mu / (double)L.S;
   out[1] = sg / (double)L.S;
+}
+
+__global__ void k_loglik_gather(const char* ws, Layout L, double* out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= L.S) return;
+  out[s] = (reinterpret_cast<const double*>(ws + L.off_aux) + (size_t)s * L.aux_doubles)[C_LOGLIK];
+}
+
+cudaError_t launch_loglik_gather(const void* ws, const Layout& L, double* out, cudaStream_t st) {
+  k_loglik_gather<<<(L.S + 127) / 128, 128, 0, st>>>(static_cast<const char*>(ws), L, out);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_sample_terms(const void* ws, const Layout& L, double* out, cudaStream_t st) {

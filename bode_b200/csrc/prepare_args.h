@@ -15,5 +15,6 @@ struct PrepArgs {
   // quadrature mode (nullable): kernel mean embedding of the observations and double integral supplied by k_rowmean
   const double* e_ovr;       // S*n   replaces xik(X)
   const double* sigma0_ovr;  // S     replaces bk
+  int loglik_only;           // 1: stop after the factorisation scalars (host MCMC likelihoods): no w, no L^-1, no tiling
 };
 }  // namespace bode

@@ -37,6 +37,7 @@ class EkldEngine:
         self.last_kernel_ms = None
         self.quad = None
         self._ndim = 0
+        self._prepared = False
 
     # ---- helpers -------------------------------------------------------------------------------------------
     def _dev(self, a, shape=None):
@@ -102,11 +103,41 @@ class EkldEngine:
                 self.quad = (Xq, wq, Nq)
             self.n, self.d, self.S = n, d, S
             self._ndim = ndim
+            self._prepared = True
             self._keep = (Xd, Yd, H)  # keep inputs alive until the stream has consumed them
         return self.info
 
+    def loglik(self, X, Y, hyp, nugget_var, jitter=GPY_JITTER):
+        """GP log marginal likelihood of every row of ``hyp`` (``get_likelihood``, ``_sampler.py:221-232``) as a host
+        NumPy array: one likelihood-only launch of the prepare kernel.  Observations are cached on the device between
+        calls with the same (X, Y) objects (the MCMC calls this thousands of times per outer iteration)."""
+        with torch.cuda.device(self.device):
+            key = (id(X), id(Y))
+            if getattr(self, "_ll_key", None) != key:
+                self._ll_X = self._dev(X)
+                self._ll_Y = self._dev(Y).reshape(-1)
+                self._ll_key = key
+                self._ll_hold = (X, Y)
+            Xd, Yd = self._ll_X, self._ll_Y
+            n, d = Xd.shape
+            H = self._dev(np.atleast_2d(hyp))
+            S, ndim = H.shape
+            nbytes = self.lib.bode_ekld_workspace_bytes(n, d, S)
+            if nbytes == 0:
+                _ext.check(-2)
+            if self.ws is None or self.ws.numel() < nbytes:
+                self.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            info = self._buf("info", S, torch.int32)[:S]
+            out = self._buf("loglik", S, torch.float64)[:S]
+            _ext.check(self.lib.bode_gp_loglik_dev(_ptr(Xd), _ptr(Yd), _ptr(H), n, d, S, ndim, float(nugget_var), float(jitter),
+                                                   _ptr(self.ws), self.ws.numel(), _ptr(info), _ptr(out), self._stream()))
+            self._prepared = False  # the workspace no longer holds a scoring state
+            return out.cpu().numpy()
+
     def sample_terms(self):
         """(S, 8) device tensor: variance, noise_var, sigma0, sigma1, mu1, logdet, Y^T A^-1 Y, loglik."""
+        if not self._prepared:
+            raise RuntimeError("call prepare() first")
         with torch.cuda.device(self.device):
             out = torch.empty((self.S, 8), dtype=torch.float64, device=self.device)
             _ext.check(self.lib.bode_ekld_sample_terms_dev(_ptr(self.ws), self.n, self.d, self.S, _ptr(out), self._stream()))
@@ -114,6 +145,8 @@ class EkldEngine:
 
     def mu_sigma(self):
         """``get_mu_sigma`` (``_sampler.py:434-444``): (mean_s mu_1, mean_s sigma_1) as Python floats."""
+        if not self._prepared:
+            raise RuntimeError("call prepare() first")
         with torch.cuda.device(self.device):
             out = torch.empty(2, dtype=torch.float64, device=self.device)
             _ext.check(self.lib.bode_ekld_mu_sigma_dev(_ptr(self.ws), self.n, self.d, self.S, _ptr(out), self._stream()))
@@ -124,7 +157,7 @@ class EkldEngine:
     def score(self, X_design, idx_offset=0, form=_ext.BODE_FORM_REFERENCE, want_var=True, timed=False):
         """Score every row of X_design (device or host array).  Returns device tensors:
         dict(score (Nd,), var (Nd,)|None, logk (S, Nd), best (1,), best_idx (1,) int64)."""
-        if self.ws is None:
+        if not self._prepared:
             raise RuntimeError("call prepare() first")
         with torch.cuda.device(self.device):
             Xd = self._dev(X_design)
@@ -161,7 +194,7 @@ class EkldEngine:
 
     def us_variance(self, X_grid, idx_offset=0):
         """Uncertainty-sampling comparator (``_sampler.py:506-514``): mean_s latent predictive variance + argmax."""
-        if self.ws is None:
+        if not self._prepared:
             raise RuntimeError("call prepare() first")
         with torch.cuda.device(self.device):
             Xg = self._dev(X_grid)

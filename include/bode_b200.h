@@ -134,6 +134,12 @@ int bode_ekld_score_host(const double* X, const double* Y, const double* hyp, in
 int bode_gp_loglik_host(const double* X, const double* Y, const double* hyp, int n, int d, int S, int ndim,
                         double nugget_var, double jitter, double* loglik);
 
+/* Device-pointer form of the same (one launch of the prepare kernel in likelihood-only mode + a gather):
+ * loglik[S] device; workspace as for bode_ekld_prepare_dev (its scoring state is NOT valid afterwards). */
+int bode_gp_loglik_dev(const double* X, const double* Y, const double* hyp, int n, int d, int S, int ndim,
+                       double nugget_var, double jitter, void* workspace, size_t workspace_bytes, int* info, double* loglik,
+                       void* stream);
+
 /* Measured FP64 peak of this GPU (DMMA.8x8x4 register-resident loop and DFMA loop), TFLOP/s; used by bench.py
  * as the roofline denominator because MEASURED_PEAKS.json has no FP64 entry. */
 int bode_fp64_peak(double* dmma_tflops, double* dfma_tflops);

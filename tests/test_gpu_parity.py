@@ -342,3 +342,15 @@ def test_quad_mode_converges_to_closed_form(engine):
     assert abs(mu_q - mu_c) < 1e-6 * abs(mu_c) and abs(sg_q - sg_c) < 1e-4 * abs(sg_c)
     keep = closed > np.median(closed)  # away from the zeros of v, where log EKLD is steep
     np.testing.assert_allclose(quad[keep], closed[keep], atol=2e-3)
+
+
+def test_engine_loglik_fast_path(engine):
+    """EkldEngine.loglik (likelihood-only launch used by the host MCMC) == oracle, and invalidates the scoring state."""
+    X, Y, Xd, hyp = cases.make_problem(4, 35, 9, 10, seed=71, ell_lo=0.2, ell_hi=0.8)
+    ll = engine.loglik(X, Y, hyp, 1e-6)
+    np.testing.assert_allclose(ll, orc.log_likelihoods(X, Y, hyp), rtol=1e-10)
+    np.testing.assert_allclose(engine.loglik(X, Y, hyp[:3], 1e-6), ll[:3], rtol=0, atol=0)  # cached observations, same bits
+    with pytest.raises(RuntimeError):
+        engine.score(Xd)
+    engine.prepare(X, Y, hyp, 1e-6)
+    assert engine.score(Xd)["score"].shape == (10,)

@@ -13,6 +13,11 @@ What changed relative to the reference, and why:
     (``:619``), ``get_mu_sigma`` honours its ``model`` argument (``:438``), the wasted ``eig_val_vec`` (``:441``)
     is dropped.  The MLE branch (``mcmc_model=False``) is signature-broken upstream (``:447, :656``) and is not
     provided.
+  * ``ekld_form`` defaults to 1: the EKLD is evaluated as -1/2 log1p(-v^2/(sigma_1 k_xx)), which is analytically identical
+    to the reference expression (``:480``) but has no 2e-16 absolute noise floor.  Under dense scoring the literal
+    expression (``ekld_form=0``) turns ~1e-7 of the entries (those with EKLD < 1e-16, the least informative
+    candidates) into NaN / -inf, and ``np.argmax`` semantics would then *select* such a candidate (measured: 19 of 1.28e8
+    entries at config 4).  The C ABI and ``EkldEngine`` keep the literal form as their default.
 Only the ARD-RBF kernel is supported (``xik`` / ``bk`` are RBF-only upstream too, ``_core.py:86-101``).
 """
 from __future__ import annotations
@@ -77,7 +82,7 @@ class KLSampler(object):
                  mcmc_model_avg=50,
                  X_design=None,
                  engine=None,
-                 ekld_form=0,
+                 ekld_form=1,
                  hyper_samples=None,
                  process_group=None,
                  ekld_mode='closed'):

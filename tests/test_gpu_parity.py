@@ -162,7 +162,7 @@ def test_single_candidate_wrapper_mcmc_kld(engine):
     import bode_b200
     X, Y, Xd, hyp = cases.make_problem(3, 15, 6, 40, seed=13, ell_lo=0.2, ell_hi=0.7)
     kls = bode_b200.KLSampler(X, Y, False, lambda x: 0.0, False, [(0, 1)] * 3, mcmc_model=True, mcmc_chains=2, mcmc_model_avg=6,
-                              mcmc_steps=40, mcmc_burn=10, mcmc_thin=5, engine=engine, hyper_samples=lambda X_, Y_, it: hyp)
+                              mcmc_steps=40, mcmc_burn=10, mcmc_thin=5, engine=engine, hyper_samples=lambda X_, Y_, it: hyp, ekld_form=0)
     for c in (0, 7, 39):
         m, v = kls.mcmc_kld(Xd[c], kls.model)
         mo, vo = orc.mcmc_kld_literal(Xd[c], X, Y, hyp, nugget=1e-3)
@@ -266,7 +266,7 @@ def test_sequential_loop_matches_oracle_loop(engine):
 
     kls = bode_b200.KLSampler(X0, Y0, False, cases.ex4_func6, False, [(0, 1)] * d, mcmc_model=True, max_it=iters, kld_tol=0.0,
                               mcmc_chains=2, mcmc_model_avg=S, mcmc_steps=100, mcmc_burn=10, mcmc_thin=5,
-                              X_design=Xd, engine=engine, hyper_samples=hyper)
+                              X_design=Xd, engine=engine, hyper_samples=hyper, ekld_form=0)
     Xg, Yg, _, kld_all, _, mu_qoi, sigma_qoi = kls.optimize(num_designs=Nd)
     # oracle loop
     X, Y = X0.copy(), Y0.copy()
@@ -373,19 +373,25 @@ def test_config4_full_size_properties(engine):
     Xd = torch.from_numpy(rng.random((Nd, d))).to(engine.device)
     engine.prepare(X, Y, hyp, 1e-6)
     assert int(engine.info.abs().max()) == 0
-    res = engine.score(Xd, want_var=False)
+    # The literal reference expression (:480) has a ~2e-16 absolute noise floor: at 1.28e8 evaluations a handful of
+    # entries whose true EKLD is < 1e-16 come out <= 0 and their log is NaN / -inf -- and np.argmax semantics then picks
+    # such a candidate.  Document it, then use the analytically identical log1p form (KLSampler's default).
+    lit = engine.score(Xd, want_var=False, form=0)["logk"]
+    n_bad = int((torch.isnan(lit) | torch.isinf(lit)).sum())
+    assert n_bad < 1000
+    res = engine.score(Xd, want_var=False, form=1)
     score = res["score"]
-    assert not bool(torch.isnan(score).any())
+    assert not bool(torch.isnan(score).any()) and not bool(torch.isinf(score).any())
     j = int(res["best_idx"].item())
     assert j == int(torch.argmax(score).item()) and float(res["best"].item()) == float(score.max().item())
     # one rank's shard of an 8-way split reproduces the same bits and the same local winner
     lo, hi = 3 * (Nd // 8), 4 * (Nd // 8)
     full_shard = score[lo:hi].clone()
-    part = engine.score(Xd[lo:hi], idx_offset=lo, want_var=False)
+    part = engine.score(Xd[lo:hi], idx_offset=lo, want_var=False, form=1)
     assert torch.equal(part["score"], full_shard)
     assert int(part["best_idx"].item()) == lo + int(torch.argmax(full_shard).item())
     # parity on a subset (plus the winner) against the oracle and the 80-bit truth
-    res = engine.score(Xd, want_var=False)
+    res = engine.score(Xd, want_var=False, form=1)
     sub = np.concatenate([rng.choice(Nd, size=47, replace=False), [j]])
     Xs = Xd[torch.from_numpy(sub).to(engine.device)].cpu().numpy()
     got = np.exp(res["logk"][:, torch.from_numpy(sub).to(engine.device)].cpu().numpy())
@@ -393,5 +399,6 @@ def test_config4_full_size_properties(engine):
     t = truth.ekld_truth(X, Y, Xs, hyp)
     assert_parity(got, ref["kld"], t["kld"], min_trusted=0.3)
     tsc = np.log(t["kld"]).mean(0)
-    assert (np.abs(res["score"].cpu().numpy()[sub] - tsc) <= 2.0 * np.mean(1e-8 + 1e-15 / t["kld"], axis=0)).all()
+    np.testing.assert_allclose(got, t["kld"], rtol=1e-7)  # log1p form: relative accuracy down to the smallest EKLD
+    assert np.abs(res["score"].cpu().numpy()[sub] - tsc).max() <= 1e-7
     assert tsc[-1] >= tsc.max() - 1e-7  # the global winner also wins within the subset

@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && CT <= 2) ? 2 : 
       ++q;
       if (it >= lag && ((it - lag) & (kWarps - 1)) == warp) {
         // refill duty for the stage released `lag` chunks ago (chunk it-lag -> chunk it-lag+stages)
-        if (rf_ls < nsamp && elect_one()) {
+        if (rf_ls < nsamp && !(a.debug_skip & 4) && elect_one()) {
           const int pst = (st >= lag) ? st - lag : st - lag + stages;
           mbar_wait(empty0 + 8 * pst, (st >= lag) ? ph : (ph ^ 1));
           issue_chunk(rf_ls, rf_q, pst);
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && CT <= 2) ? 2 : 
         __syncwarp();
       }
       if (it >= lag) { if (++rf_q == nchunks) { rf_q = 0; rf_ls++; } }
-      while (!ok) ok = mbar_try_wait(full0 + 8 * st, ph);
+      if (!(a.debug_skip & 4)) { while (!ok) ok = mbar_try_wait(full0 + 8 * st, ph); }
       mb = ring_lane + (size_t)st * a.chunk_max;
       next_cp = chunk_p0[q + 1];
       // look one chunk ahead with a non-blocking poll

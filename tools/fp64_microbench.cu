@@ -178,16 +178,17 @@ __global__ void k_exp_check(double* err, int n) {
 }
 
 // smem-fed DMMA: warp tile RT row-tiles x CT col-tiles; per k4-step loads RT A-frags + CT B-frags (LDS.64)
-template <int RT, int CT>
-__global__ void __launch_bounds__(256) k_dmma_smem(double* out, int iters, long long* cyc) {
+template <int RT, int CT, int NT = 256>
+__global__ void __launch_bounds__(NT) k_dmma_smem(double* out, int iters, long long* cyc) {
   extern __shared__ double sm[];
   const int KG = 16;  // k4 groups resident
   double* sA = sm;                          // [KG][RT*8 rows][4]
-  double* sB = sm + KG * RT * 32 * 4;       // [KG][CT*8 cols * 2 col-groups][4]
-  for (int i = threadIdx.x; i < KG * RT * 32 * 4 + KG * CT * 8 * 2 * 4; i += blockDim.x) sm[i] = 1e-3 * (i % 97);
+  constexpr int NCG = (NT == 256) ? 2 : 4;
+  double* sB = sm + KG * RT * 32 * 4;       // [KG][CT*8 cols * NCG col-groups][4]
+  for (int i = threadIdx.x; i < KG * RT * 32 * 4 + KG * CT * 8 * NCG * 4; i += blockDim.x) sm[i] = 1e-3 * (i % 97);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int rg = warp & 3, cg = warp >> 2;
+  const int rg = (NT == 256) ? (warp & 3) : (warp >> 2), cg = (NT == 256) ? (warp >> 2) : (warp & 3);
   double c0[RT][CT], c1[RT][CT];
 #pragma unroll
   for (int r = 0; r < RT; r++)
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(256) k_dmma_smem(double* out, int iters, long 
     for (int g = 0; g < KG; g++) {
       double a[RT], b[CT];
       const double* pa = sA + (g * RT * 32 + rg * RT * 8) * 4 + lane;  // rows (lane/4), k (lane%4) contiguous 256B per tile
-      const double* pb = sB + (g * CT * 16 + cg * CT * 8) * 4 + lane;
+      const double* pb = sB + (g * CT * 8 * NCG + cg * CT * 8) * 4 + lane;
 #pragma unroll
       for (int r = 0; r < RT; r++) a[r] = pa[r * 32];
 #pragma unroll
@@ -297,6 +298,17 @@ int main(int argc, char** argv) {
     size_t sh14 = (16 * 1 * 32 * 4 + 16 * 4 * 16 * 4) * 8;
     CK(cudaFuncSetAttribute(k_dmma_smem<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh14));
     RUN("dmma_smem_rt1_ct4_occ1x256", 16 * 1 * 4 * 16, ISM, 1, 256, (k_dmma_smem<1, 4><<<grid, 256, sh14>>>(out, ISM, cyc)));
+    {
+      size_t sh = (16 * 8 * 32 * 4 + 16 * 2 * 8 * 4 * 4) * 8;
+      CK(cudaFuncSetAttribute(k_dmma_smem<8, 2, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+      RUN("dmma_smem_rt8_ct2_occ1x512_16warps", 16 * 8 * 2 * 16, ISM, 1, 512, (k_dmma_smem<8, 2, 512><<<grid, 512, sh>>>(out, ISM, cyc)));
+      size_t sh2 = (16 * 2 * 32 * 4 + 16 * 2 * 8 * 4 * 4) * 8;
+      CK(cudaFuncSetAttribute(k_dmma_smem<2, 2, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh2));
+      RUN("dmma_smem_rt2_ct2_occ1x512_16warps", 16 * 2 * 2 * 16, ISM, 1, 512, (k_dmma_smem<2, 2, 512><<<grid, 512, sh2>>>(out, ISM, cyc)));
+      size_t sh1 = (16 * 1 * 32 * 4 + 16 * 2 * 8 * 4 * 4) * 8;
+      CK(cudaFuncSetAttribute(k_dmma_smem<1, 2, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh1));
+      RUN("dmma_smem_rt1_ct2_occ1x512_16warps", 16 * 1 * 2 * 16, ISM, 1, 512, (k_dmma_smem<1, 2, 512><<<grid, 512, sh1>>>(out, ISM, cyc)));
+    }
     size_t sh82 = (16 * 8 * 32 * 4 + 16 * 2 * 16 * 4) * 8;
     CK(cudaFuncSetAttribute(k_dmma_smem<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh82));
     RUN("dmma_smem_rt8_ct2_occ1x256", 16 * 8 * 2 * 16, ISM, 1, 256, (k_dmma_smem<8, 2><<<grid, 256, sh82>>>(out, ISM, cyc)));

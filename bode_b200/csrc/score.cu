@@ -567,16 +567,11 @@ static void assign_tiles(int nrt, int nrg, int rt_cap, short* tile_id /*[kMaxRG]
     for (int t = 0; t < cnt[g]; t++) tile_id[g * kMaxRT + (rt_cap - 1 - t)] = tmp[g][t];
 }
 
-static int plan_variant(const Layout& L, size_t smem_limit, ScorePlan* P) {
+static int plan_chunks(const Layout& L, size_t smem_limit, size_t chunk_max, ScorePlan* P) {
   const int nrt = L.nrt;
-  const int C = P->cg * P->ct * 8;
-  P->C = C;
+  const int C = P->C;
   // chunk plan: consecutive PAIRS of k4 groups (both groups of a pair share their first stored row tile), greedily
   // packed up to the chunk size
-  const size_t pair0_doubles = (size_t)nrt * 64;
-  size_t chunk_max = 2048;  // 16 KB
-  if (const char* ck = getenv("BODE_CHUNK_KB")) chunk_max = (size_t)atoi(ck) * 128;  // tuning knob
-  if (chunk_max < pair0_doubles) chunk_max = pair0_doubles;
   int nch = 0;
   int g = 0;
   P->chunk_g0[0] = 0;
@@ -609,6 +604,31 @@ static int plan_variant(const Layout& L, size_t smem_limit, ScorePlan* P) {
   P->u_global = u_global;
   P->stages = stages;
   P->smem = score_smem_bytes(L, C, P->rg, nthreads, stages, (int)chunk_max, nch, u_global);
+  return 0;
+}
+
+static int plan_variant(const Layout& L, size_t smem_limit, ScorePlan* P) {
+  P->C = P->cg * P->ct * 8;
+  const size_t pair0_doubles = (size_t)L.nrt * 64;
+  if (const char* ck = getenv("BODE_CHUNK_KB")) {  // tuning knob
+    size_t cm = (size_t)atoi(ck) * 128;
+    return plan_chunks(L, smem_limit, cm < pair0_doubles ? pair0_doubles : cm, P);
+  }
+  // Every chunk transition costs each warp ~450 cycles of barrier bookkeeping, so prefer few large chunks (two 40 KB
+  // stages measured best at config 3); fall back to smaller chunks when shared memory is short or U must stay global.
+  const size_t sizes_kb[] = {40, 32, 24, 16};
+  ScorePlan best = *P;
+  bool have = false;
+  for (size_t kb : sizes_kb) {
+    size_t cm = kb * 128;
+    if (cm < pair0_doubles) cm = pair0_doubles;
+    ScorePlan T = *P;
+    if (plan_chunks(L, smem_limit, cm, &T) != 0) continue;
+    if (!have || (best.u_global && !T.u_global)) { best = T; have = true; }
+    if (!T.u_global) break;  // largest chunk size that keeps U in shared memory
+  }
+  if (!have) return -1;
+  *P = best;
   return 0;
 }
 

@@ -658,7 +658,7 @@ int plan_score(const Layout& L, int64_t Nd, int sm_count, size_t smem_optin, Sco
   // work items: (tile, sample chunk); aim for >= 16 waves of CTAs, keep at least 4 samples per item when possible
   const int64_t ntiles = (Nd + C - 1) / C;
   int sc = L.S;
-  int waves = 16;
+  int waves = 40;
   if (const char* wv = getenv("BODE_WAVES")) waves = atoi(wv);  // tuning knob
   const int64_t target = (int64_t)waves * sm_count;
   while (sc > 4 && ntiles * ((L.S + sc - 1) / sc) < target) sc = (sc + 1) / 2;

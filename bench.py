@@ -318,8 +318,8 @@ def main():
                        "l2": "flushed between timed iterations (256 MB write)", "sharding": "candidate blocks, %d per rank" % Nd,
                        "wall_s_timed_region": wall},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak["dmma_tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / peak["dmma_tflops"], "traffic": 24202240,
-                         "traffic_unit": "bytes per launch (dram__bytes_read.sum 18.20 MB + dram__bytes_write.sum 6.01 MB; the 51 MB of "
+                         "frac": achieved / peak["dmma_tflops"], "traffic": 26968064,
+                         "traffic_unit": "bytes per launch (dram__bytes_read.sum 18.16 MB + dram__bytes_write.sum 8.80 MB; the 51 MB of "
                                          "log-EKLD output mostly stays in the 126 MB L2 during the launch)",
                          "traffic_source": "profiles/r1_k_score_bench_ncu_raw.txt: ncu --set full of this command, k_score launch",
                          "kernel": "bode::k_score (FP64 tensor pipe, DMMA.8x8x4)", "kernel_ms": k_ms,

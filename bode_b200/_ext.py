@@ -22,7 +22,7 @@ EXPORTS = (
     "bode_version", "bode_strerror", "bode_last_cuda_error", "bode_ekld_workspace_bytes", "bode_ekld_prepare_dev",
     "bode_ekld_sample_terms_dev", "bode_ekld_mu_sigma_dev", "bode_ekld_score_scratch_bytes", "bode_ekld_score_dev",
     "bode_ekld_score_dev_timed", "bode_us_variance_dev", "bode_quad_scratch_bytes", "bode_quad_rowmean_dev",
-    "bode_ekld_prepare_quad_dev", "bode_ekld_score_quad_dev", "bode_ekld_score_host", "bode_gp_loglik_host", "bode_gp_loglik_dev", "bode_fp64_peak",
+    "bode_ekld_prepare_quad_dev", "bode_ekld_score_quad_dev", "bode_ekld_score_host", "bode_gp_loglik_host", "bode_gp_loglik_dev", "bode_ekld_plan_describe", "bode_fp64_peak",
 )
 
 
@@ -94,6 +94,9 @@ def load():
     lib.bode_gp_loglik_dev.restype = ctypes.c_int
     lib.bode_gp_loglik_dev.argtypes = [c_dp, c_dp, c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                        ctypes.c_double, ctypes.c_double, c_dp, ctypes.c_size_t, c_dp, c_dp, c_dp]
+    lib.bode_ekld_plan_describe.restype = ctypes.c_int
+    lib.bode_ekld_plan_describe.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int,
+                                            ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t]
     lib.bode_fp64_peak.restype = ctypes.c_int
     lib.bode_fp64_peak.argtypes = [c_dp, c_dp]
     _lib = lib
@@ -152,6 +155,15 @@ def gp_loglik_host(X, Y, hyp, nugget_var, jitter=1e-8):
     check(lib.bode_gp_loglik_host(_np_ptr(X), _np_ptr(Y), _np_ptr(hyp), n, d, S, ndim, float(nugget_var), float(jitter),
                                   _np_ptr(out)))
     return out
+
+
+def plan_describe(n, d, S, Nd, sm_count=148, smem_optin=232448):
+    """Launch plan (dict) of the scoring kernel for a shape; host-only, works without a GPU."""
+    import json
+    lib = load()
+    buf = ctypes.create_string_buffer(1 << 16)
+    check(lib.bode_ekld_plan_describe(int(n), int(d), int(S), int(Nd), int(sm_count), int(smem_optin), buf, len(buf)))
+    return json.loads(buf.value.decode())
 
 
 def fp64_peak():

@@ -372,6 +372,30 @@ int bode_gp_loglik_host(const double* X, const double* Y, const double* hyp, int
   return BODE_OK;
 }
 
+int bode_ekld_plan_describe(int n, int d, int S, int64_t Nd, int sm_count, size_t smem_optin, char* out, size_t cap) {
+  if (!out || cap < 64 || !shape_ok(n, d, S) || Nd < 1 || sm_count < 1) return BODE_ERR_BAD_ARG;
+  if (!shape_supported(n, d)) return BODE_ERR_UNSUPPORTED;
+  const Layout L = make_layout(n, d, S);
+  ScorePlan P;
+  if (plan_score(L, Nd, sm_count, smem_optin, &P) != 0) return BODE_ERR_UNSUPPORTED;
+  int w = snprintf(out, cap,
+                   "{\"variant\": %d, \"row_groups\": %d, \"col_groups\": %d, \"row_tiles_per_warp\": %d, \"col_tiles_per_warp\": %d, "
+                   "\"candidates_per_cta\": %d, \"threads\": %d, \"samples_per_item\": %d, \"tiles\": %d, \"items\": %lld, "
+                   "\"stages\": %d, \"chunk_doubles\": %d, \"u_global\": %d, \"smem_bytes\": %zu, \"nrt\": %d, \"ng\": %d, \"chunk_g0\": [",
+                   P.variant, P.rg, P.cg, P.rt, P.ct, P.C, 32 * P.rg * P.cg, P.sc, P.ntiles, (long long)P.nitems, P.stages, P.chunk_max,
+                   P.u_global, P.smem, L.nrt, L.ng);
+  for (int q = 0; q <= P.nchunks && w > 0 && (size_t)w < cap; q++)
+    w += snprintf(out + w, cap - w, "%s%d", q ? ", " : "", (int)P.chunk_g0[q]);
+  if (w > 0 && (size_t)w < cap) w += snprintf(out + w, cap - w, "], \"tile_id\": [");
+  for (int g = 0; g < P.rg && w > 0 && (size_t)w < cap; g++) {
+    w += snprintf(out + w, cap - w, "%s[", g ? ", " : "");
+    for (int t = 0; t < P.rt && (size_t)w < cap; t++) w += snprintf(out + w, cap - w, "%s%d", t ? ", " : "", (int)P.tile_id[g * kMaxRT + t]);
+    if ((size_t)w < cap) w += snprintf(out + w, cap - w, "]");
+  }
+  if (w > 0 && (size_t)w < cap) w += snprintf(out + w, cap - w, "]}");
+  return (w > 0 && (size_t)w < cap) ? BODE_OK : BODE_ERR_BAD_ARG;
+}
+
 int bode_fp64_peak(double* dmma_tflops, double* dfma_tflops) {
   if (!dmma_tflops || !dfma_tflops) return BODE_ERR_BAD_ARG;
   BODE_CUDA(measure_fp64_peak(dmma_tflops, dfma_tflops));

@@ -140,6 +140,11 @@ int bode_gp_loglik_dev(const double* X, const double* Y, const double* hyp, int 
                        double nugget_var, double jitter, void* workspace, size_t workspace_bytes, int* info, double* loglik,
                        void* stream);
 
+/* Host-only: JSON description of the launch plan the scoring entry points would use for this shape on a device with
+ * `sm_count` SMs and `smem_optin` bytes of opt-in shared memory per CTA (kernel variant, candidates per CTA, ring
+ * chunks, row-tile assignment, work items).  No CUDA call is made. */
+int bode_ekld_plan_describe(int n, int d, int S, int64_t Nd, int sm_count, size_t smem_optin, char* out, size_t cap);
+
 /* Measured FP64 peak of this GPU (DMMA.8x8x4 register-resident loop and DFMA loop), TFLOP/s; used by bench.py
  * as the roofline denominator because MEASURED_PEAKS.json has no FP64 entry. */
 int bode_fp64_peak(double* dmma_tflops, double* dfma_tflops);

@@ -65,3 +65,43 @@ def test_no_cpu_fallback_without_gpu(built_lib):
     import bode_b200
     with pytest.raises(RuntimeError):
         bode_b200.KLSampler(np.random.rand(3, 1), np.random.rand(3, 1), False, lambda x: 0.0, False, [(0, 1)], mcmc_model=True)
+
+
+@pytest.mark.parametrize("n", [1, 3, 8, 9, 30, 64, 200, 256, 257, 500, 512, 513, 700, 1000, 1024])
+def test_launch_plans_are_consistent(built_lib, n):
+    """Host-side planning of the scoring kernel (no GPU needed): every row tile is assigned exactly once, ring chunks are
+    whole pairs of k4 groups covering all groups, the shared-memory request fits a B200 CTA, work items cover S."""
+    from bode_b200 import _ext
+    S, Nd = 64, 100000
+    p = _ext.plan_describe(n, 8, S, Nd)
+    nrt = (n + 7) // 8
+    assert p["nrt"] == nrt and p["ng"] == 2 * nrt
+    tiles = sorted(t for row in p["tile_id"] for t in row if t >= 0)
+    assert tiles == list(range(nrt))
+    for row in p["tile_id"]:  # right-aligned, ascending
+        live = [t for t in row if t >= 0]
+        assert live == sorted(live) and row[len(row) - len(live):] == live
+    loads = [sum(t + 1 for t in row if t >= 0) for row in p["tile_id"]]
+    assert max(loads) <= 1.25 * (sum(loads) / len(loads)) + nrt  # LPT balance of the triangular work
+    g0 = p["chunk_g0"]
+    assert g0[0] == 0 and g0[-1] == 2 * nrt and all(b > a and b % 2 == 0 for a, b in zip(g0, g0[1:]))
+    blocks = lambda a, b: sum(nrt - (g >> 1) for g in range(a, b)) * 32
+    assert all(blocks(a, b) <= p["chunk_doubles"] for a, b in zip(g0, g0[1:]))
+    assert p["smem_bytes"] <= 232448 and p["stages"] >= 2 and p["threads"] == 512
+    assert p["candidates_per_cta"] == p["col_groups"] * p["col_tiles_per_warp"] * 8
+    assert p["tiles"] == -(-Nd // p["candidates_per_cta"])
+    assert p["items"] == p["tiles"] * -(-S // p["samples_per_item"])
+    assert p["items"] >= 148
+
+
+def test_launch_plan_small_problem_uses_all_sms(built_lib):
+    from bode_b200 import _ext
+    p = _ext.plan_describe(200, 8, 64, 1000)      # 16 tiles only: split the hyper-samples to fill the GPU
+    assert p["items"] >= 148 and p["samples_per_item"] < 64
+    q = _ext.plan_describe(200, 8, 2, 100)        # tiny: cannot fill, must still be valid
+    assert q["items"] == 2 * 2 and q["samples_per_item"] == 1
+    lib = _ext.load()
+    import ctypes
+    buf = ctypes.create_string_buffer(4096)
+    assert lib.bode_ekld_plan_describe(2000, 8, 4, 10, 148, 232448, buf, 4096) == -2
+    assert lib.bode_ekld_plan_describe(10, 8, 4, 10, 148, 232448, buf, 8) == -1

@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && CT <= 2) ? 2 : 
   const uint32_t empty0 = full0 + 8 * kMaxStages;                 // empty[stages]: all warps are done with the stage
   const uint32_t aux_full = empty0 + 8 * kMaxStages;
   int* chunk_off = reinterpret_cast<int*>(bars + 2 * kMaxStages + 1);  // [nchunks+1] offset (doubles) of chunk q inside M_s
-  int* chunk_p0 = chunk_off + nchunks + 1;                              // [nchunks+1] first group PAIR of chunk q
+  int* chunk_p0 = chunk_off + nchunks + 1;                              // [nchunks+2] first group PAIR of chunk q
 
   // ---- work item ----
   const int item = blockIdx.x;
@@ -272,6 +272,7 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && CT <= 2) ? 2 : 
     chunk_off[q] = (int)m_goff(nrt, a.chunk_g0[q]);
     chunk_p0[q] = (q < nchunks) ? (a.chunk_g0[q] >> 1) : 0x7fffffff;
   }
+  if (tid == 0) chunk_p0[nchunks + 1] = 0x7fffffff;  // read-ahead slot
   // candidate tile -> smem, dimension-major (rows beyond Nd are filled with a harmless interior point)
   for (int idx = tid; idx < C * kXtStride; idx += kThreads) {
     const int k = idx / C, c = idx - k * C;
@@ -335,7 +336,7 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && CT <= 2) ? 2 : 
     else { ga_lo = n0 + (jq - 1) * per + min(jq - 1, extra); ga_hi = ga_lo + per + ((jq - 1) < extra ? 1 : 0); }
   }
   int st = 0, it = 0;
-  uint32_t ph = 0, ok = 0;
+  uint32_t ph = 0;
   // refills trail the consumer by `lag` chunks so that the duty warp rarely has to wait for slower warps
   const int lag = (stages >= 4) ? 2 : 1;
   // refill cursor: (sample, chunk) that goes into the stage released by chunk it-lag, i.e. chunk it-lag+stages
@@ -369,7 +370,7 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && CT <= 2) ? 2 : 
 #pragma unroll
       for (int ct = 0; ct < CT; ct++) { acc[t][ct][0] = 0.0; acc[t][ct][1] = 0.0; }
 
-    int q = -1, p = 0, next_cp = 0;
+    int q = -1, p = 0, next_cp = 0, next_cp_pref = chunk_p0[1];
     const double* mb = ring_lane;
     const double* kb = kc_lane;
     auto enter = [&]() {  // start chunk q+1 (ring stage st)
@@ -384,12 +385,10 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && CT <= 2) ? 2 : 
         __syncwarp();
       }
       if (it >= lag) { if (++rf_q == nchunks) { rf_q = 0; rf_ls++; } }
-      if (!(a.debug_skip & 4)) { while (!ok) ok = mbar_try_wait(full0 + 8 * st, ph); }
+      next_cp = next_cp_pref;               // prefetched one transition ago (its shared-memory latency is off the path)
+      next_cp_pref = chunk_p0[q + 2];
+      if (!(a.debug_skip & 4)) mbar_wait(full0 + 8 * st, ph);
       mb = ring_lane + (size_t)st * a.chunk_max;
-      next_cp = chunk_p0[q + 1];
-      // look one chunk ahead with a non-blocking poll
-      const int nst = (st + 1 == stages) ? 0 : st + 1;
-      ok = mbar_test_wait(full0 + 8 * nst, (st + 1 == stages) ? (ph ^ 1) : ph);
     };
     auto leave = [&]() {  // done with chunk q
       __syncwarp();
@@ -545,7 +544,7 @@ static size_t score_smem_bytes(const Layout& L, int C, int RG, int nthreads, int
   size_t dbl = (size_t)L.npad * C + (u_global ? (size_t)aux_u(L) : L.aux_doubles) + (size_t)stages * chunk_max + (size_t)RG * C + 4 * (size_t)nthreads +
                (size_t)C * kXtStride;
   return dbl * sizeof(double) + sizeof(uint64_t) * (2 * kMaxStages + 1) +
-         sizeof(int) * (2 * (nchunks + 1) + 8) + 128;
+         sizeof(int) * (2 * (nchunks + 2) + 8) + 128;
 }
 
 // Longest-processing-time assignment of row tiles (weight R+1 ~ number of live k4 groups) to the row groups.

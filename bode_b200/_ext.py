@@ -62,7 +62,7 @@ def load():
     lib.bode_ekld_mu_sigma_dev.restype = ctypes.c_int
     lib.bode_ekld_mu_sigma_dev.argtypes = [c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_dp, c_dp]
     lib.bode_ekld_score_scratch_bytes.restype = ctypes.c_size_t
-    lib.bode_ekld_score_scratch_bytes.argtypes = [ctypes.c_int64]
+    lib.bode_ekld_score_scratch_bytes.argtypes = [ctypes.c_int64, ctypes.c_int]
     lib.bode_ekld_score_dev.restype = ctypes.c_int
     lib.bode_ekld_score_dev.argtypes = [c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_dp, ctypes.c_int64,
                                         ctypes.c_int64, ctypes.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]

@@ -21,6 +21,8 @@ cudaError_t launch_mu_sigma(const void* ws, const Layout& L, double* out, cudaSt
 cudaError_t launch_loglik_gather(const void* ws, const Layout& L, double* out, cudaStream_t st);
 int plan_score(const Layout& L, int64_t Nd, int sm_count, size_t smem_optin, ScorePlan* P);
 cudaError_t launch_score(const ScoreArgs& a, const ScorePlan& P, cudaStream_t st);
+cudaError_t launch_ekld(const void* ws, const Layout& L, double* logk, const double* vplane, int S, int64_t Nd, int form,
+                        cudaStream_t st);
 cudaError_t launch_reduce(const double* logk, int S, int64_t Nd, int64_t idx_offset, double* score, double* var,
                           double* part_val, int64_t* part_idx, double* best, int64_t* best_idx, cudaStream_t st);
 cudaError_t launch_exp_inplace(double* v, size_t n, cudaStream_t st);
@@ -209,10 +211,14 @@ int bode_ekld_mu_sigma_dev(const void* workspace, int n, int d, int S, double* o
   return BODE_OK;
 }
 
-size_t bode_ekld_score_scratch_bytes(int64_t Nd) {
-  if (Nd < 1) return 0;
+static size_t score_partials_bytes(int64_t Nd) {
   const size_t nb = (size_t)((Nd + 255) / 256);
   return align_up(nb * sizeof(double), 256) + align_up(nb * sizeof(int64_t), 256);
+}
+
+size_t bode_ekld_score_scratch_bytes(int64_t Nd, int S) {
+  if (Nd < 1 || S < 1) return 0;
+  return score_partials_bytes(Nd) + align_up(sizeof(double) * (size_t)S * (size_t)Nd, 256);  // argmax partials + v plane
 }
 
 static int score_common(const void* workspace, int n, int d, int S, const double* Xd, int64_t Nd, int64_t idx_offset,
@@ -230,12 +236,11 @@ static int score_common(const void* workspace, int n, int d, int S, const double
   if (plan_score(L, Nd, props.sm_count, props.smem_optin, &P) != 0) return BODE_ERR_UNSUPPORTED;
   ScoreArgs a;
   a.ws = workspace; a.L = L; a.Xd = Xd; a.Nd = Nd; a.logk = logk; a.S = S; a.xi_ovr = xi_ovr;
+  a.vplane = reinterpret_cast<double*>(static_cast<char*>(scratch) + score_partials_bytes(Nd));
   a.sc = P.sc; a.ntiles = P.ntiles; a.form = form; a.mode = mode;
   {
     const char* dbg = getenv("BODE_DEBUG_SKIP");
     a.debug_skip = dbg ? atoi(dbg) : 0;
-    const char* eg = getenv("BODE_EPI_GROUPS");
-    a.epi_groups = eg ? atoi(eg) : 3;
   }
   a.stages = P.stages; a.chunk_max = P.chunk_max; a.nchunks = P.nchunks; a.u_global = P.u_global;
   memcpy(a.chunk_g0, P.chunk_g0, sizeof(a.chunk_g0));
@@ -249,6 +254,7 @@ static int score_common(const void* workspace, int n, int d, int S, const double
   }
   BODE_CUDA(launch_score(a, P, st));
   if (kernel_ms) BODE_CUDA(cudaEventRecord(ev1, st));
+  if (mode == kModeEkld) BODE_CUDA(launch_ekld(workspace, L, logk, a.vplane, S, Nd, form, st));
   const size_t nb = (size_t)((Nd + 255) / 256);
   double* part_val = static_cast<double*>(scratch);
   int64_t* part_idx = reinterpret_cast<int64_t*>(static_cast<char*>(scratch) + align_up(nb * sizeof(double), 256));
@@ -314,7 +320,7 @@ int bode_ekld_score_host(const double* X, const double* Y, const double* hyp, in
   BODE_CUDA(dVar.alloc(sizeof(double) * Nd));
   BODE_CUDA(dBest.alloc(sizeof(double)));
   BODE_CUDA(dBestIdx.alloc(sizeof(int64_t)));
-  BODE_CUDA(dScr.alloc(bode_ekld_score_scratch_bytes(Nd)));
+  BODE_CUDA(dScr.alloc(bode_ekld_score_scratch_bytes(Nd, S)));
   BODE_CUDA(dMs.alloc(2 * sizeof(double)));
   BODE_CUDA(cudaMemcpy(dX.p, X, sizeof(double) * n * d, cudaMemcpyHostToDevice));
   BODE_CUDA(cudaMemcpy(dY.p, Y, sizeof(double) * n, cudaMemcpyHostToDevice));
@@ -403,3 +409,19 @@ int bode_fp64_peak(double* dmma_tflops, double* dfma_tflops) {
 }
 
 }  // extern "C"
+
+#ifdef BODE_TIMELINE
+#include <stdio.h>
+namespace bode { cudaError_t debug_copy_timeline(long long* host); cudaError_t debug_set_phase_a(int v); }
+extern "C" int bode_debug_phase_a(int v) { return bode::debug_set_phase_a(v) == cudaSuccess ? 0 : -4; }
+extern "C" int bode_debug_dump(const char* path) {
+  static long long buf[8 * 16 * 16 * 14];
+  if (cudaDeviceSynchronize() != cudaSuccess) return -4;
+  if (bode::debug_copy_timeline(buf) != cudaSuccess) return -4;
+  FILE* f = fopen(path, "wb");
+  if (!f) return -1;
+  fwrite(buf, sizeof(long long), 8 * 16 * 16 * 14, f);
+  fclose(f);
+  return 0;
+}
+#endif

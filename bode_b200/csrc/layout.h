@@ -3,11 +3,16 @@
 // Per hyper-sample s the workspace holds
 //   aux[s]   : one contiguous block (copied to shared memory with a single bulk copy by the scoring kernel)
 //                consts[8]  = {variance, noise_var, sigma0, sigma1, mu1, logdet, Y^T A^-1 Y, loglik}
-//                ck[16]     = 1/(sqrt(2) ell_k)            (zero padded)
+//                ck[16]     = 1/(sqrt(2) ell_k)            (zero padded; arguments of erf in xik)
 //                ell[16]    = ell_k                        (one padded)
-//                tab[32]    = variance * 2^(j/32)         (table of rbf_exp, see rbf.h)
-//                w[npad]    = A^-1 e                       (zero padded)
-//                U[npad][dpad] = X[j][k] * ck[k]           (zero padded rows / columns)
+//                cks[16]    = 2 kappa min(ck, ck_max)      (zero padded; kappa^2 = 64/ln 2, see rbf.h)
+//                tabr[64][16] = variance * 2^(j/64), each entry replicated 16 times so that lane l reads copy l & 15:
+//                               the per-lane table lookups of a warp never collide on a shared-memory bank
+//                nw[npad][2] = {-|U_j|^2, (A^-1 e)_j}      (zero padded)
+//                Ut[nrt][dk][32] = U = kappa min(ck, ck_max)[k] * (X[j][k] - 1/2) in mma.m8n8k4 A-fragment order:
+//                               entry lane = rr*4 + kk of block (R, i) is U[8R + rr][4i + kk]   (zero padded)
+//              so that the cross-covariance tile of 8 observations x 8 candidates is
+//                  z = -|U_j|^2 - |y|^2 + 2 U_j . y   (dk DMMAs, y = the candidate scaled like U),   k = tab-exp2(z / 64).
 //   M[s]     : L_s^-1 in the "k4-group major, live row-tile suffix" tiling the DMMA mainloop consumes:
 //                for g = 0..ng-1 (columns j = 4g..4g+3), for R = g/2..nrt-1 (rows 8R..8R+7): a 256-byte block
 //                holding M[8R+rr][4g+kk] at [rr*4 + kk] -- exactly the A-fragment order of mma.m8n8k4.f64.
@@ -28,7 +33,9 @@ namespace bode {
 
 constexpr int kConsts = 8;
 constexpr int kCkPad = 16;
-constexpr int kTabPad = 32;
+constexpr int kTabPad = 32;   // table of rbf_exp (quadrature row means)
+constexpr int kTab64 = 64;    // table of rbf_exp64 (Gram matrix and cross-covariances)
+constexpr int kTabRep = 16;   // bank-staggered copies of each table entry in the aux block
 enum ConstIdx { C_SS = 0, C_NOISE = 1, C_SIGMA0 = 2, C_SIGMA1 = 3, C_MU1 = 4, C_LOGDET = 5, C_QUAD = 6, C_LOGLIK = 7 };
 
 struct Layout {
@@ -36,7 +43,7 @@ struct Layout {
   int nrt;   // row tiles of 8
   int npad;  // 8 * nrt
   int ng;    // k4 groups = 2 * nrt
-  int dpad;  // d rounded up to even (16-byte rows of U)
+  int dk;    // k4 steps of the cross-covariance dot product = ceil(d / 4)
   size_t aux_doubles;  // per sample
   size_t m_doubles;    // per sample
   size_t lw_doubles;   // per sample
@@ -52,8 +59,8 @@ BODE_HD Layout make_layout(int n, int d, int S) {
   L.nrt = (n + 7) / 8;
   L.npad = 8 * L.nrt;
   L.ng = 2 * L.nrt;
-  L.dpad = (d + 1) & ~1;
-  L.aux_doubles = (size_t)kConsts + 2 * kCkPad + kTabPad + L.npad + (size_t)L.npad * L.dpad;
+  L.dk = (d + 3) / 4;
+  L.aux_doubles = (size_t)kConsts + 3 * kCkPad + kTab64 * kTabRep + 2 * (size_t)L.npad + (size_t)L.npad * 4 * L.dk;
   L.m_doubles = (size_t)32 * L.nrt * (L.nrt + 1);
   L.lw_doubles = (size_t)(n + 2) * L.npad;
   L.xw_doubles = (size_t)n * L.npad;
@@ -68,9 +75,10 @@ BODE_HD Layout make_layout(int n, int d, int S) {
 // aux sub-offsets (doubles)
 BODE_HD int aux_ck() { return kConsts; }
 BODE_HD int aux_ell() { return kConsts + kCkPad; }
-BODE_HD int aux_tab() { return kConsts + 2 * kCkPad; }
-BODE_HD int aux_w() { return kConsts + 2 * kCkPad + kTabPad; }
-BODE_HD int aux_u(const Layout& L) { return kConsts + 2 * kCkPad + kTabPad + L.npad; }
+BODE_HD int aux_cks() { return kConsts + 2 * kCkPad; }
+BODE_HD int aux_tabr() { return kConsts + 3 * kCkPad; }
+BODE_HD int aux_nw() { return kConsts + 3 * kCkPad + kTab64 * kTabRep; }   // nw and Ut may stay in global memory (large n)
+BODE_HD int aux_ut(const Layout& L) { return aux_nw() + 2 * L.npad; }
 
 // offset (doubles) of k4-group g inside a sample's tiled M; block (R, g), R >= g/2, sits at m_goff(g) + (R - g/2)*32
 BODE_HD size_t m_goff(int nrt, int g) {

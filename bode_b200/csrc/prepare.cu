@@ -96,23 +96,28 @@ __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
   double* rdiag = Ld + kNB * kNB;          // [8] reciprocals of the diagonal of Ld
   double* red = rdiag + kNB;               // [8] reduction scratch
   double* ck = red + 8;                    // [16]
-  double* tab = ck + kCkPad;               // [32] variance * 2^(j/32)
-  double* vec = tab + kTabPad;             // [npad] back-substitution right-hand side
+  double* cku = ck + kCkPad;               // [16] kappa * min(ck, ck_max): scale of U (rbf.h)
+  double* tab = cku + kCkPad;              // [64] variance * 2^(j/64)
+  double* vec = tab + kTab64;              // [npad] back-substitution right-hand side
   __shared__ int fail;
 
   double* aux = reinterpret_cast<double*>(a.ws + a.L.off_aux) + (size_t)s * a.L.aux_doubles;
   double* Mt = reinterpret_cast<double*>(a.ws + a.L.off_m) + (size_t)s * a.L.m_doubles;
   double* Lw = reinterpret_cast<double*>(a.ws + a.L.off_lw) + (size_t)s * a.L.lw_doubles;
   double* Xw = reinterpret_cast<double*>(a.ws + a.L.off_xw) + (size_t)s * a.L.xw_doubles;
-  double* U = aux + aux_u(a.L);
-  const int dpad = a.L.dpad;
+  double* Ut = aux + aux_ut(a.L);   // U in A-fragment tiles (layout.h)
+  const int dk = a.L.dk;
 
   const double* h = a.hyp + (size_t)s * a.ndim;
   const double ss = h[0];
   const double noise = (a.ndim == d + 2) ? h[d + 1] * h[d + 1] : a.nugget_var;
   const double SQRT2 = 1.4142135623730951, SQRTPI = 1.7724538509055159;
-  if (tid < kCkPad) ck[tid] = (tid < d) ? 1.0 / (SQRT2 * h[1 + tid]) : 0.0;
-  if (tid >= 32 && tid < 32 + kTabPad) tab[tid - 32] = ss * exp2((double)(tid - 32) / 32.0);
+  if (tid < kCkPad) {
+    const double c = (tid < d) ? 1.0 / (SQRT2 * h[1 + tid]) : 0.0;
+    ck[tid] = c;
+    cku[tid] = kKappa * fmin(c, kCkMax);
+  }
+  if (tid >= 32 && tid < 32 + kTab64) tab[tid - 32] = ss * exp2((double)(tid - 32) / 64.0);
   if (tid == 0) {
     // hyper-parameter sanity: the scoring kernel's exponent arithmetic assumes a sane variance scale
     int bad = !(ss > 9.5e-7 && ss < 1.0e6) || !(noise >= 0.0 && noise < 1.0e6);
@@ -123,13 +128,25 @@ __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
   if (tid < kCkPad) {
     aux[aux_ck() + tid] = ck[tid];
     aux[aux_ell() + tid] = (tid < d) ? h[1 + tid] : 1.0;
+    aux[aux_cks() + tid] = 2.0 * cku[tid];
   }
-  if (tid >= 32 && tid < 32 + kTabPad) aux[aux_tab() + tid - 32] = tab[tid - 32];
+  for (int idx = tid; idx < kTab64 * kTabRep; idx += kPrepThreads) aux[aux_tabr() + idx] = tab[idx / kTabRep];
 
-  // ---- prescaled coordinates U, bordered rows e = xik(X) (row n) and Y (row n+1) ----------------------------
-  for (int idx = tid; idx < npad * dpad; idx += kPrepThreads) {
-    const int j = idx / dpad, k = idx - j * dpad;
-    U[idx] = (j < n && k < d) ? a.X[(size_t)j * d + k] * ck[k] : 0.0;
+  // ---- prescaled, centred coordinates U (fragment-tiled), -|U_j|^2, bordered rows e = xik(X) (row n) and Y (row n+1)
+  for (int idx = tid; idx < npad * 4 * dk; idx += kPrepThreads) {
+    const int blk = idx >> 5, ln = idx & 31;          // block (R, i), lane = rr*4 + kk
+    const int R = blk / dk, i = blk - R * dk;
+    const int j = 8 * R + (ln >> 2), k = 4 * i + (ln & 3);
+    Ut[idx] = (j < n && k < d) ? (a.X[(size_t)j * d + k] - 0.5) * cku[k] : 0.0;
+  }
+  for (int j = tid; j < npad; j += kPrepThreads) {  // fixed order over k
+    double nun = 0.0;
+    if (j < n)
+      for (int k = 0; k < d; k++) {
+        const double u = (a.X[(size_t)j * d + k] - 0.5) * cku[k];
+        nun = fma(-u, u, nun);
+      }
+    aux[aux_nw() + 2 * j] = nun;
   }
   for (int j = tid; j < npad; j += kPrepThreads) {
     double e = 0.0, y = 0.0;
@@ -149,27 +166,27 @@ __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
   __syncthreads();
   // ---- A = K + (noise + jitter) I, lower triangle, rows 0..n-1 ------------------------------------------------
   // strictly-lower entries, flat triangular index so that all threads carry the same number of exp() calls
-  // (U is staged in the panel buffer, free until the factorisation starts, when it fits: the entries are gathers)
-  const bool u_smem = dpad <= kNB;
-  if (u_smem) {
-    for (int idx = tid; idx < npad * dpad; idx += kPrepThreads) Ljp[idx] = U[idx];
+  // (the observations are staged in the panel buffer, free until the factorisation starts, when they fit)
+  const bool x_smem = d <= kNB;
+  if (x_smem) {
+    for (int idx = tid; idx < n * d; idx += kPrepThreads) Ljp[idx] = a.X[idx];
     __syncthreads();
   }
-  const double* Us = u_smem ? Ljp : U;
+  const double* Xs = x_smem ? Ljp : a.X;
   const int ntri = n * (n - 1) / 2;
   for (int idx = tid; idx < ntri; idx += kPrepThreads) {
     int i = (int)((1.0 + sqrt(1.0 + 8.0 * (double)idx)) * 0.5);
     while (i * (i - 1) / 2 > idx) i--;
     while ((i + 1) * i / 2 <= idx) i++;
     const int j = idx - i * (i - 1) / 2;
-    const double* ui = Us + (size_t)i * dpad;
-    const double* uj = Us + (size_t)j * dpad;
-    double r2 = 0.0;
+    const double* xi = Xs + (size_t)i * d;
+    const double* xj = Xs + (size_t)j * d;
+    double z = 0.0;
     for (int k = 0; k < d; k++) {
-      const double t = ui[k] - uj[k];
-      r2 = fma(t, t, r2);
+      const double t = (xi[k] - xj[k]) * cku[k];
+      z = fma(-t, t, z);
     }
-    Lw[(size_t)i * npad + j] = rbf_exp(-r2, tab);
+    Lw[(size_t)i * npad + j] = rbf_exp64<1>(z, tab);
   }
   for (int idx = tid; idx < n * npad; idx += kPrepThreads) {
     const int i = idx / npad, j = idx - i * npad;
@@ -260,7 +277,7 @@ __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
       cst[C_LOGDET] = qnan; cst[C_QUAD] = qnan; cst[C_LOGLIK] = -INFINITY;
       a.info[s] = info;
     }
-    for (int j = tid; j < npad; j += kPrepThreads) aux[aux_w() + j] = 0.0;
+    for (int j = tid; j < npad; j += kPrepThreads) aux[aux_nw() + 2 * j + 1] = 0.0;
     for (size_t idx = tid; idx < a.L.m_doubles; idx += kPrepThreads) Mt[idx] = 0.0;
     return;
   }
@@ -325,7 +342,7 @@ __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
     }
     __syncthreads();
   }
-  for (int j = tid; j < npad; j += kPrepThreads) aux[aux_w() + j] = (j < n) ? vec[j] : 0.0;
+  for (int j = tid; j < npad; j += kPrepThreads) aux[aux_nw() + 2 * j + 1] = (j < n) ? vec[j] : 0.0;
 
   // ---- phase 2: X = I L^-T  (row r of X = column r of L^-1), same panel machinery -------------------------------
   for (int j0 = 0; j0 < n; j0 += kNB) {
@@ -373,7 +390,7 @@ __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
 }
 
 size_t prepare_smem_bytes(const Layout& L) {
-  return sizeof(double) * ((size_t)L.npad * kNB + kNB * kNB + kNB + 8 + kCkPad + kTabPad + L.npad);
+  return sizeof(double) * ((size_t)L.npad * kNB + kNB * kNB + kNB + 8 + 2 * kCkPad + kTab64 + L.npad);
 }
 
 cudaError_t launch_prepare(const PrepArgs& a, cudaStream_t st) {

@@ -55,4 +55,68 @@ __device__ __forceinline__ double sqdist(const double* __restrict__ uj, const do
   return r2;
 }
 
+// ---- variance * 2^(z/64): the form the Gram matrix (K1) and the cross-covariances (K2) use -----------------------
+// The coordinates are pre-scaled by kappa / (sqrt2 ell), kappa^2 = 64/ln2, so that
+// exp(-r^2) = 2^(z/64) with z = -|u - y|^2 in the scaled coordinates.  k = rint(z) splits z = k + f, |f| <= 1/2
+// exactly (no Cody-Waite constants needed); 2^(f/64) - 1 is a degree-5 Taylor polynomial in f (truncation 3.5e-17
+// relative), the 64-entry table holds variance * 2^(j/64) and 2^(k>>6) goes into the exponent field: 9 FP64-pipe
+// operations, no branches.  Valid for z in (-2^31, ~0]; the result saturates at variance * 2^-1000 for z < -64000.
+constexpr int kExpTab64 = 64;
+constexpr double kKappa = 9.608979270291599;      // sqrt(64 / ln 2)
+constexpr double kCkMax = 707.10678118654755;      // 1/(sqrt2 * 1e-3): lengthscales below 1e-3 of the unit box are
+                                                   // evaluated as 1e-3 in the covariance (keeps |z| < 2^31)
+
+// REP = stride between consecutive table entries (1: plain table; 16: the bank-staggered copies of layout.h, with
+// `tab` already offset by the lane's copy index)
+template <int REP>
+__device__ __forceinline__ double rbf_exp64(double z, const double* __restrict__ tab) {
+  const double SHIFT = 6755399441055744.0;  // 1.5 * 2^52
+  const double t = z + SHIFT;
+  const double kf = t - SHIFT;
+  const double f = z - kf;
+  const int k = __double2loint(t);
+  // c_i = (ln2/64)^i / i!
+  double p = fma(f, 1.2417843701716925e-12, 5.732851688640402e-10);
+  p = fma(p, f, 2.1173137155464776e-07);
+  p = fma(p, f, 5.86490495505617e-05);
+  p = fma(p, f, 0.010830424696249145);
+  const double q = p * f;
+  const double T = tab[(k & (kExpTab64 - 1)) * REP];
+  const double res = fma(T, q, T);
+  const int e = max(k >> 6, -1000);
+  return __hiloint2double(__double2hiint(res) + (e << 20), __double2loint(res));
+}
+
+// N independent evaluations written stage by stage (the N dependency chains interleave in the instruction stream)
+template <int N, int REP>
+__device__ __forceinline__ void rbf_exp64_n(const double* __restrict__ z, const double* __restrict__ tab, double* __restrict__ out) {
+  const double SHIFT = 6755399441055744.0;
+  double t[N], f[N], p[N], T[N];
+  int k[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) t[i] = z[i] + SHIFT;
+#pragma unroll
+  for (int i = 0; i < N; i++) { k[i] = __double2loint(t[i]); T[i] = tab[(k[i] & (kExpTab64 - 1)) * REP]; }
+#pragma unroll
+  for (int i = 0; i < N; i++) t[i] = t[i] - SHIFT;
+#pragma unroll
+  for (int i = 0; i < N; i++) f[i] = z[i] - t[i];
+#pragma unroll
+  for (int i = 0; i < N; i++) p[i] = fma(f[i], 1.2417843701716925e-12, 5.732851688640402e-10);
+#pragma unroll
+  for (int i = 0; i < N; i++) p[i] = fma(p[i], f[i], 2.1173137155464776e-07);
+#pragma unroll
+  for (int i = 0; i < N; i++) p[i] = fma(p[i], f[i], 5.86490495505617e-05);
+#pragma unroll
+  for (int i = 0; i < N; i++) p[i] = fma(p[i], f[i], 0.010830424696249145);
+#pragma unroll
+  for (int i = 0; i < N; i++) p[i] = p[i] * f[i];
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    const double res = fma(T[i], p[i], T[i]);
+    const int e = max(k[i] >> 6, -1000);
+    out[i] = __hiloint2double(__double2hiint(res) + (e << 20), __double2loint(res));
+  }
+}
+
 }  // namespace bode

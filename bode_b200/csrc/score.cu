@@ -9,12 +9,13 @@
 //     v   = xi - w_s.k                           (K3, folded into phase A)
 //     EKLD = log(sqrt(s1)/sqrt(s2)) + s2/(2 s1) + (v^2/s1/(sigma_x+noise))*0.5 - 0.5 ; logk = log(EKLD)   (K4)
 //
-// Work decomposition: one CTA = one work item = (tile of C candidates) x (chunk of SC hyper-samples).  Per
-// sample the CTA runs phase A (8 compute warps fill Kc[npad][C] in shared memory), phase B (each warp owns up to
-// RT row tiles x CT column tiles of T = L^-1 Kc as DMMA accumulators; L^-1 streams through a shared-memory ring
-// filled by a dedicated producer warp with 1-D bulk copies (TMA, cp.async.bulk + mbarrier)), and a small epilogue.
-// log EKLD goes to logk[S][Nd]; a second kernel reduces over s sequentially (deterministic, independent of how
-// candidates were tiled or sharded across GPUs) and does the block argmax; a third picks the global winner.
+// Work decomposition: one CTA = one work item = (tile of C candidates) x (chunk of SC hyper-samples).  Per sample the
+// CTA runs phase A (all 16 warps build Kc[npad][C] in shared memory: the distance part on the FP64 tensor pipe, the
+// exponential on the FP64 pipe), phase B (each warp owns up to RT row tiles x CT column tiles of T = L^-1 Kc as DMMA
+// accumulators; L^-1 streams through a shared-memory ring filled with 1-D bulk copies (TMA, cp.async.bulk + mbarrier)
+// by a rotating duty warp), and a short combine that writes sigma_x and v.  k_ekld turns those into log EKLD (K4),
+// k_reduce sums over s sequentially (deterministic, independent of how candidates were tiled or sharded across GPUs)
+// and does the block argmax, k_final_argmax picks the winner.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -81,6 +82,13 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
 }
+// volatile variant: keeps the issue order written in the source (independent accumulators interleaved) -- the
+// scheduler otherwise chains the dependent DMMAs of one tile back to back
+__device__ __forceinline__ void dmma884_ordered(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
 template <int NT>
 __device__ __forceinline__ void compute_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
 // one lane of a converged warp (no thread-id arithmetic, no S2R in hot loops)
@@ -90,62 +98,162 @@ __device__ __forceinline__ bool elect_one() {
   return p != 0;
 }
 
+// Developer timeline (tools/ts_run.py builds an out-of-tree copy with -DBODE_TIMELINE): clock64 stamps of 8 work items
+// x 16 warps x 16 samples x 8 events, plus the cycles each warp spent waiting on the ring per sample.
+#ifdef BODE_TIMELINE
+#ifndef BODE_TS_BASE
+#define BODE_TS_BASE 2000
+#endif
+__device__ long long g_ts[8 * 16 * 16 * 8];
+__device__ int g_dbg_a;  // phase-A decomposition switches of the developer build: 8 no DMMA, 16 no exp, 32 no Kc store, 64 no loads
+cudaError_t debug_set_phase_a(int v) { return cudaMemcpyToSymbol(g_dbg_a, &v, sizeof(int)); }
+__device__ long long g_tw[8 * 16 * 16 * 2];
+__device__ long long g_ta[8 * 16 * 16 * 4];
+#define TS_STAMP(ev) do { if (ts_on && lane == 0 && ls < 16) g_ts[((ts_item * 16 + warp) * 16 + ls) * 8 + (ev)] = clock64(); } while (0)
+#define TS_WAIT_BEGIN() long long tw0_ = clock64()
+#define TS_WAIT_END(k) do { tw_acc[k] += clock64() - tw0_; } while (0)
+#define DBG_PARAM , int dbg, long long* tsa
+#define DBG_ARG , dbg, tsa
+#define TSA(i) do { if (tsa && (threadIdx.x & 31) == 0) tsa[i] = clock64(); } while (0)
+cudaError_t debug_copy_timeline(long long* host /* 8*16*16*10 */) {
+  cudaError_t e = cudaMemcpyFromSymbol(host, g_ts, sizeof(g_ts));
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpyFromSymbol(host + 8 * 16 * 16 * 8, g_tw, sizeof(g_tw));
+  if (e != cudaSuccess) return e;
+  return cudaMemcpyFromSymbol(host + 8 * 16 * 16 * 10, g_ta, sizeof(g_ta));
+}
+#else
+#define TS_STAMP(ev) do { } while (0)
+#define TS_WAIT_BEGIN() do { } while (0)
+#define TS_WAIT_END(k) do { } while (0)
+#define DBG_PARAM
+#define DBG_ARG
+#define TSA(i) do { } while (0)
+#endif
+
 // ----------------------------------------------------------------------------------------------------------------
-// Phase A: Kc[(g*C + c)*4 + kk] = ss * exp(-sum_k (U[4g+kk][k] - x_c[k] ck[k])^2); partial w.k; partial xik factors
+// Phase A: the cross-covariance tile Kc = k(X, candidates of this CTA) on the FP64 tensor pipe.
+//   z[j][c] = -|U_j|^2 - |y_c|^2 + 2 U_j . y_c   (scaled coordinates of layout.h / rbf.h; DK DMMAs per 8 x 8 tile, the
+//             A fragments come pre-tiled from the prepare kernel, the B fragments live in registers for the sample)
+//   k[j][c] = variance * 2^(z/64)                 (9 FP64 operations, table lookups on bank-staggered copies)
+// Warp w owns column tile w % NCT and the row tiles R == w / NCT (mod NRS); partial w.k per candidate; the xik factors
+// (closed form, 2d erf per candidate) are spread over all threads as (candidate, dimension slice).
+//
+// Kc block (g, column tile) holds the 4 x 8 values of k4 group g in B-fragment order for phase B: position
+// kk + 4 * n with  n = q + 4e  for tile column 2q + e -- a fixed permutation of the 8 candidates of a tile that makes
+// these stores conflict-free (the accumulator column n of phase B belongs to tile column 2 (n & 3) + (n >> 2)).
 // ----------------------------------------------------------------------------------------------------------------
-template <int DP, int C, int NT>
-__device__ __forceinline__ void phase_a(const double* __restrict__ aux, const double* __restrict__ U, int dpad, int g_lo, int g_hi, int d,
-                                        const double* __restrict__ xt, double* __restrict__ Kc,
-                                        double* __restrict__ pv, double* __restrict__ xip, int tid) {
+template <int DK, int NB>
+__device__ __forceinline__ void phase_a_batch(const double2* __restrict__ nw, const double* __restrict__ ut_lane, int R, int rstride,
+                                              int r, const double (&yb)[DK], const double (&nyn)[2],
+                                              const double* __restrict__ tab_lane, double (&wk)[2], double* __restrict__ kst,
+                                              int kstride DBG_PARAM) {
+  double acc[NB][2], wv[NB], af[NB][DK];
+#pragma unroll
+  for (int t = 0; t < NB; t++) {
+    const int Rt = R + t * rstride;
+#ifdef BODE_TIMELINE
+    if (dbg & 64) { wv[t] = 1.0; acc[t][0] = nyn[0]; acc[t][1] = nyn[1]; for (int i = 0; i < DK; i++) af[t][i] = nyn[0]; continue; }
+#endif
+    const double2 v = nw[8 * Rt + r];
+    wv[t] = v.y;
+    acc[t][0] = v.x + nyn[0];
+    acc[t][1] = v.x + nyn[1];
+#pragma unroll
+    for (int i = 0; i < DK; i++) af[t][i] = ut_lane[(size_t)(Rt * DK + i) * 32];
+  }
+#pragma unroll
+  for (int i = 0; i < DK; i++)
+#pragma unroll
+    for (int t = 0; t < NB; t++) {
+#ifdef BODE_TIMELINE
+      if (dbg & 8) { acc[t][0] += af[t][i]; continue; }
+#endif
+      dmma884_ordered(acc[t][0], acc[t][1], af[t][i], yb[i]);
+    }
+  double kv[2 * NB];
+#ifdef BODE_TIMELINE
+  if (dbg & 16) { for (int i = 0; i < 2 * NB; i++) kv[i] = (&acc[0][0])[i]; } else
+#endif
+  rbf_exp64_n<2 * NB, kTabRep>(&acc[0][0], tab_lane, kv);
+#pragma unroll
+  for (int t = 0; t < NB; t++) {
+    wk[0] = fma(wv[t], kv[2 * t], wk[0]);
+    wk[1] = fma(wv[t], kv[2 * t + 1], wk[1]);
+    double* dst = kst + (size_t)(R + t * rstride) * kstride;
+#ifdef BODE_TIMELINE
+    if (dbg & 32) continue;
+#endif
+    dst[0] = kv[2 * t];
+    dst[16] = kv[2 * t + 1];
+  }
+}
+
+template <int DK, int C, int NT>
+__device__ __forceinline__ void phase_a(const double* __restrict__ aux, const double* __restrict__ nwp, const double* __restrict__ Ut,
+                                        int nrt, int d, const double* __restrict__ xt, double* __restrict__ Kc,
+                                        double* __restrict__ pv, int tid DBG_PARAM) {
+  constexpr int NW = NT / 32, NCT = C / 8, NRS = NW / NCT;
+  static_assert(NW % NCT == 0, "warps must split evenly over the column tiles");
+  const int warp = tid >> 5, lane = tid & 31;
+  const int ctile = warp % NCT, rs = warp / NCT;
+  const int r = lane >> 2, q = lane & 3;
+  const double* cks = aux + aux_cks();
+  const double* tab_lane = aux + aux_tabr() + (lane & (kTabRep - 1));
+  // B fragments (dimension 4i + q of candidate 8 ctile + r), doubled scaled coordinates
+  double yb[DK];
+#pragma unroll
+  for (int i = 0; i < DK; i++) yb[i] = (xt[(4 * i + q) * C + 8 * ctile + r] - 0.5) * cks[4 * i + q];
+  // -|y|^2 of the two candidates this thread's accumulators belong to (tile columns 2q, 2q + 1), fixed order over k
+  // (the padded dimensions k >= d have cks = 0 and add exact zeros)
+  double nyn[2] = {0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < 4 * DK; k++) {
+    const double c2 = cks[k];
+    const double t0 = (xt[k * C + 8 * ctile + 2 * q] - 0.5) * c2, t1 = (xt[k * C + 8 * ctile + 2 * q + 1] - 0.5) * c2;
+    nyn[0] = fma(-t0, t0, nyn[0]);
+    nyn[1] = fma(-t1, t1, nyn[1]);
+  }
+  nyn[0] *= 0.25;
+  nyn[1] *= 0.25;
+  TSA(0);
+  double wk[2] = {0.0, 0.0};
+  const double2* nw = reinterpret_cast<const double2*>(nwp);
+  const double* ut_lane = Ut + lane;
+  // element (row r of tile R, tile column 2q + e) -> block (2R + (r >> 2), ctile), position (r & 3) + 4q + 16e
+  double* kst = Kc + (size_t)((r >> 2) * NCT + ctile) * 32 + (r & 3) + 4 * q;
+  constexpr int kstride = 2 * NCT * 32;
+  // the first row slice also runs the per-candidate combine of the previous sample (threads < C): it gets the
+  // short end of the split
+  int R = NRS - 1 - rs;
+  for (; R + 3 * NRS < nrt; R += 4 * NRS) phase_a_batch<DK, 4>(nw, ut_lane, R, NRS, r, yb, nyn, tab_lane, wk, kst, kstride DBG_ARG);
+  const int left = (R < nrt) ? (nrt - R + NRS - 1) / NRS : 0;
+  if (left == 3) phase_a_batch<DK, 3>(nw, ut_lane, R, NRS, r, yb, nyn, tab_lane, wk, kst, kstride DBG_ARG);
+  else if (left == 2) phase_a_batch<DK, 2>(nw, ut_lane, R, NRS, r, yb, nyn, tab_lane, wk, kst, kstride DBG_ARG);
+  else if (left == 1) phase_a_batch<DK, 1>(nw, ut_lane, R, NRS, r, yb, nyn, tab_lane, wk, kst, kstride DBG_ARG);
+  TSA(1);
+  // partial w.k of this warp's rows: sum over the 8 row lanes (fixed tree), one slot per (row slice, candidate)
+#pragma unroll
+  for (int o = 4; o < 32; o <<= 1) {
+    wk[0] += __shfl_xor_sync(0xffffffffu, wk[0], o);
+    wk[1] += __shfl_xor_sync(0xffffffffu, wk[1], o);
+  }
+  if (lane < 4) {
+    pv[rs * C + 8 * ctile + 2 * q] = wk[0];
+    pv[rs * C + 8 * ctile + 2 * q + 1] = wk[1];
+  }
+  TSA(2);
+}
+
+// xik(x) = variance * prod_k sqrt(pi)/sqrt(2) * ell_k * (erf((1-x_k) ck) - erf((0-x_k) ck))  (reference _core.py:86-92):
+// thread (candidate c, slice jq) multiplies the factors of the dimensions k == jq (mod NJQ)
+template <int C, int NT>
+__device__ __forceinline__ void xik_factors(const double* __restrict__ aux, int d, const double* __restrict__ xt,
+                                            double* __restrict__ xip, int tid) {
   constexpr int NJQ = NT / C;
-  const int c = tid % C, jq = tid / C;
   const double* ck = aux + aux_ck();
   const double* ell = aux + aux_ell();
-  const double* tab = aux + aux_tab();
-  const double* w = aux + aux_w();
-  double y[DP];
-#pragma unroll
-  for (int k = 0; k < DP; k++) y[k] = xt[k * C + c] * ck[k];
-  double wk = 0.0;
-  int g = g_lo;
-  // this thread slice owns the k4 groups [g_lo, g_hi); two groups (8 independent exp chains) per iteration
-  constexpr int GS = 1;  // stride between the two groups of an iteration
-  for (; g + GS < g_hi; g += 2 * GS) {
-    double r2[8];
-#pragma unroll
-    for (int kk = 0; kk < 4; kk++) {
-      r2[kk] = sqdist<DP>(U + (size_t)(4 * g + kk) * dpad, y);
-      r2[4 + kk] = sqdist<DP>(U + (size_t)(4 * (g + GS) + kk) * dpad, y);
-    }
-    double kv[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) kv[i] = rbf_exp(-r2[i], tab);
-    const double2 wa = *reinterpret_cast<const double2*>(w + 4 * g);
-    const double2 wb = *reinterpret_cast<const double2*>(w + 4 * g + 2);
-    const double2 wc = *reinterpret_cast<const double2*>(w + 4 * (g + GS));
-    const double2 wd = *reinterpret_cast<const double2*>(w + 4 * (g + GS) + 2);
-    wk = fma(wa.x, kv[0], wk); wk = fma(wa.y, kv[1], wk); wk = fma(wb.x, kv[2], wk); wk = fma(wb.y, kv[3], wk);
-    wk = fma(wc.x, kv[4], wk); wk = fma(wc.y, kv[5], wk); wk = fma(wd.x, kv[6], wk); wk = fma(wd.y, kv[7], wk);
-    double2* d0 = reinterpret_cast<double2*>(Kc + ((size_t)g * C + c) * 4);
-    d0[0] = make_double2(kv[0], kv[1]);
-    d0[1] = make_double2(kv[2], kv[3]);
-    double2* d1 = reinterpret_cast<double2*>(Kc + ((size_t)(g + GS) * C + c) * 4);
-    d1[0] = make_double2(kv[4], kv[5]);
-    d1[1] = make_double2(kv[6], kv[7]);
-  }
-  if (g < g_hi) {
-    double kv[4];
-#pragma unroll
-    for (int kk = 0; kk < 4; kk++) kv[kk] = rbf_exp(-sqdist<DP>(U + (size_t)(4 * g + kk) * dpad, y), tab);
-    const double2 wa = *reinterpret_cast<const double2*>(w + 4 * g);
-    const double2 wb = *reinterpret_cast<const double2*>(w + 4 * g + 2);
-    wk = fma(wa.x, kv[0], wk); wk = fma(wa.y, kv[1], wk); wk = fma(wb.x, kv[2], wk); wk = fma(wb.y, kv[3], wk);
-    double2* d0 = reinterpret_cast<double2*>(Kc + ((size_t)g * C + c) * 4);
-    d0[0] = make_double2(kv[0], kv[1]);
-    d0[1] = make_double2(kv[2], kv[3]);
-  }
-  pv[jq * C + c] = wk;
-  // xik factors of the dimensions k == jq (mod NJQ): sqrt(pi)/sqrt(2) * ell_k * (erf((1-x) ck) - erf((0-x) ck))
+  const int c = tid % C, jq = tid / C;
   double xf = 1.0;
   for (int k = jq; k < d; k += NJQ) {
     const double x = xt[k * C + c];
@@ -155,18 +263,13 @@ __device__ __forceinline__ void phase_a(const double* __restrict__ aux, const do
 }
 
 template <int C, int NT>
-__device__ __forceinline__ void phase_a_dispatch(const double* aux, const double* U, int dpad, int g_lo, int g_hi, int d,
-                                                 const double* xt, double* Kc, double* pv, double* xip, int tid) {
-  switch (d) {
-#define BODE_CASE(D)                                                          \
-  case D:                                                                     \
-    phase_a<D, C, NT>(aux, U, dpad, g_lo, g_hi, d, xt, Kc, pv, xip, tid);         \
-    break;
-    BODE_CASE(1) BODE_CASE(2) BODE_CASE(3) BODE_CASE(4) BODE_CASE(5) BODE_CASE(6) BODE_CASE(7) BODE_CASE(8)
-    BODE_CASE(9) BODE_CASE(10) BODE_CASE(11) BODE_CASE(12) BODE_CASE(13) BODE_CASE(14) BODE_CASE(15) BODE_CASE(16)
-#undef BODE_CASE
-    default:
-      break;
+__device__ __forceinline__ void phase_a_dispatch(const double* aux, const double* nwp, const double* Ut, int nrt, int d, int dk,
+                                                 const double* xt, double* Kc, double* pv, int tid DBG_PARAM) {
+  switch (dk) {
+    case 1: phase_a<1, C, NT>(aux, nwp, Ut, nrt, d, xt, Kc, pv, tid DBG_ARG); break;
+    case 2: phase_a<2, C, NT>(aux, nwp, Ut, nrt, d, xt, Kc, pv, tid DBG_ARG); break;
+    case 3: phase_a<3, C, NT>(aux, nwp, Ut, nrt, d, xt, Kc, pv, tid DBG_ARG); break;
+    default: phase_a<4, C, NT>(aux, nwp, Ut, nrt, d, xt, Kc, pv, tid DBG_ARG); break;
   }
 }
 
@@ -240,11 +343,11 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && CT <= 2) ? 2 : 
   // ---- shared memory carve-up (offsets in doubles; everything 16-byte aligned) ----
   double* Kc = reinterpret_cast<double*>(smem_raw);             // [ng][C][4]
   double* auxs = Kc + (size_t)npad * C;                          // aux block of the current sample
-  const int aux_smem_doubles = a.u_global ? aux_u(L) : (int)L.aux_doubles;  // U may stay in global memory
+  const int aux_smem_doubles = a.u_global ? aux_nw() : (int)L.aux_doubles;  // nw and Ut may stay in global memory
   double* ring = auxs + aux_smem_doubles;                        // [stages][chunk_max]
   double* red = ring + (size_t)stages * a.chunk_max;             // [RG][C]
-  double* pv = red + RG * C;                                     // [2][NJQ][C]   (NJQ*C = kThreads)
-  double* xip = pv + 2 * kThreads;                               // [2][NJQ][C]
+  double* pv = red + RG * C;                                     // [2][NRS][C]   (NRS*C = 8 * kWarps)
+  double* xip = pv + 2 * 8 * kWarps;                             // [2][NJQ][C]   (NJQ*C = kThreads)
   double* xt = xip + 2 * kThreads;                               // [kXtStride][C]  candidate tile, dimension-major
   uint64_t* bars = reinterpret_cast<uint64_t*>(xt + C * kXtStride);
   const uint32_t full0 = smem_u32(bars);                          // full[stages]: TMA completion per ring stage
@@ -321,20 +424,7 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && CT <= 2) ? 2 : 
   const double* kc_lane = Kc + (size_t)cbase * 4 + lane;
   const double* ring_lane = ring + lane;
 
-  const int aux_u_off = aux_u(L);
-  // phase-A split of the ng k4 groups over the NJQ thread slices.  Slice 0 (threads < C) also runs the per-candidate
-  // epilogue of the previous sample, a ~3000-cycle dependent chain (div, sqrt, log): it gets kEpiGroups fewer groups
-  // so that the epilogue hides under the other slices' phase A instead of delaying the post-A barrier.
-  int ga_lo, ga_hi;
-  {
-    const int kEpiGroups = a.epi_groups;
-    const int jq = tid / C;
-    const int n0 = (ng >= 4 * NJQ) ? max(0, ng / NJQ - kEpiGroups) : ng / NJQ;
-    const int rest = ng - n0, per = (NJQ > 1) ? rest / (NJQ - 1) : 0, extra = (NJQ > 1) ? rest - per * (NJQ - 1) : 0;
-    if (NJQ == 1) { ga_lo = 0; ga_hi = ng; }
-    else if (jq == 0) { ga_lo = 0; ga_hi = n0; }
-    else { ga_lo = n0 + (jq - 1) * per + min(jq - 1, extra); ga_hi = ga_lo + per + ((jq - 1) < extra ? 1 : 0); }
-  }
+  const int aux_ut_off = aux_ut(L);
   int st = 0, it = 0;
   uint32_t ph = 0;
   // refills trail the consumer by `lag` chunks so that the duty warp rarely has to wait for slower warps
@@ -343,20 +433,41 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && CT <= 2) ? 2 : 
   int rf_ls = 0, rf_q = 0;
   for (int i = 0; i < stages; i++) if (++rf_q == nchunks) { rf_q = 0; rf_ls++; }
 
+#ifdef BODE_TIMELINE
+  const int ts_item = (int)blockIdx.x - BODE_TS_BASE;
+  const bool ts_on = ts_item >= 0 && ts_item < 8 && kWarps <= 16;
+  const int dbg = g_dbg_a;
+#endif
   for (int ls = 0; ls < nsamp; ls++) {
+#ifdef BODE_TIMELINE
+    long long tw_acc[2] = {0, 0};
+#endif
+    TS_STAMP(0);
     const int par = ls & 1;
-    double* pvp = pv + par * kThreads;
+    double* pvp = pv + par * 8 * kWarps;
     double* xipp = xip + par * kThreads;
     // ---- phase A ----
     mbar_wait(aux_full, (uint32_t)par);
-    double ss = 0, noise = 0, sigma1 = 0;
-    if (tid < C) { ss = auxs[C_SS]; noise = auxs[C_NOISE]; sigma1 = auxs[C_SIGMA1]; }
+    TS_STAMP(1);
+#ifdef BODE_TIMELINE
+    long long* tsa = (ts_on && ls < 16) ? &g_ta[((ts_item * 16 + warp) * 16 + ls) * 4] : nullptr;
+#endif
+    double ss = 0;
+    if (tid < C) ss = auxs[C_SS];
     if (!((a.debug_skip & 1) && ls > 0)) {
-      // two call sites so that the U loads stay address-space specific (LDS vs LDG) instead of generic
-      if (a.u_global) phase_a_dispatch<C, kThreads>(auxs, aux_g + (size_t)ls * L.aux_doubles + aux_u_off, L.dpad, ga_lo, ga_hi, L.d, xt, Kc, pvp, xipp, tid);
-      else phase_a_dispatch<C, kThreads>(auxs, auxs + aux_u_off, L.dpad, ga_lo, ga_hi, L.d, xt, Kc, pvp, xipp, tid);
+      // two call sites so that the fragment loads stay address-space specific (LDS vs LDG) instead of generic
+      if (a.u_global) {
+        const double* ag = aux_g + (size_t)ls * L.aux_doubles;
+        phase_a_dispatch<C, kThreads>(auxs, ag + aux_nw(), ag + aux_ut_off, nrt, L.d, L.dk, xt, Kc, pvp, tid DBG_ARG);
+      } else {
+        phase_a_dispatch<C, kThreads>(auxs, auxs + aux_nw(), auxs + aux_ut_off, nrt, L.d, L.dk, xt, Kc, pvp, tid DBG_ARG);
+      }
+      TS_STAMP(5);  // (developer timeline: slot 5 = cross-covariance done, overwritten by nothing else)
+      if (!a.xi_ovr) xik_factors<C, kThreads>(auxs, L.d, xt, xipp, tid);
     }
+    TS_STAMP(2);
     __syncthreads();
+    TS_STAMP(3);
     // every warp is done with the aux block: fetch the next sample's while phase B runs
     if (tid == 0 && ls + 1 < nsamp) {
       mbar_arrive_expect_tx(aux_full, aux_bytes);
@@ -379,7 +490,9 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && CT <= 2) ? 2 : 
         // refill duty for the stage released `lag` chunks ago (chunk it-lag -> chunk it-lag+stages)
         if (rf_ls < nsamp && !(a.debug_skip & 4) && elect_one()) {
           const int pst = (st >= lag) ? st - lag : st - lag + stages;
+          TS_WAIT_BEGIN();
           mbar_wait(empty0 + 8 * pst, (st >= lag) ? ph : (ph ^ 1));
+          TS_WAIT_END(1);
           issue_chunk(rf_ls, rf_q, pst);
         }
         __syncwarp();
@@ -387,7 +500,9 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && CT <= 2) ? 2 : 
       if (it >= lag) { if (++rf_q == nchunks) { rf_q = 0; rf_ls++; } }
       next_cp = next_cp_pref;               // prefetched one transition ago (its shared-memory latency is off the path)
       next_cp_pref = chunk_p0[q + 2];
+      TS_WAIT_BEGIN();
       if (!(a.debug_skip & 4)) mbar_wait(full0 + 8 * st, ph);
+      TS_WAIT_END(0);
       mb = ring_lane + (size_t)st * a.chunk_max;
     };
     auto leave = [&]() {  // done with chunk q
@@ -400,6 +515,7 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && CT <= 2) ? 2 : 
     if (!(a.debug_skip & 2)) PhaseB<RT, CT, 0>::run(acc, toff, pend, p, next_cp, mb, kb, nrt, C, enter, leave);
     while (q + 1 < nchunks) { leave(); enter(); }  // chunks past this warp's last live row tile
     leave();
+    TS_STAMP(4);
 
     // ---- column sums of squares over this warp's rows -> red[rg][c] ----
 #pragma unroll
@@ -416,41 +532,67 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && CT <= 2) ? 2 : 
         p1 += __shfl_xor_sync(0xffffffffu, p1, o);
       }
       if (lane < 4) {
-        red[rg * C + cbase + ct * 8 + 2 * lane] = p0;
-        red[rg * C + cbase + ct * 8 + 2 * lane + 1] = p1;
+        // accumulator columns n = 2 lane, 2 lane + 1 hold tile columns 2 (n & 3) + (n >> 2) (phase A's store order)
+        const int col0 = (lane < 2) ? 4 * lane : 4 * lane - 7;
+        red[rg * C + cbase + ct * 8 + col0] = p0;
+        red[rg * C + cbase + ct * 8 + col0 + 2] = p1;
       }
     }
     __syncthreads();
+    TS_STAMP(6);
 
-    // ---- K4 epilogue: one thread per candidate ----
+    // ---- per-candidate combine: sigma_x = ss - |L^-1 k|^2 and v = xi - w.k (the EKLD itself is evaluated by k_ekld) ----
     if (tid < C) {
       double tt = red[tid];
 #pragma unroll
       for (int r = 1; r < RG; r++) tt += red[r * C + tid];
+      constexpr int NRS = kWarps / (C / 8);
       double wk = 0.0, xf = 1.0;
 #pragma unroll
-      for (int j = 0; j < NJQ; j++) { wk += pvp[j * C + tid]; xf *= xipp[j * C + tid]; }
-      const double xi = a.xi_ovr ? ((c0 + tid < a.Nd) ? a.xi_ovr[(size_t)(s_begin + ls) * a.Nd + c0 + tid] : 0.0) : ss * xf;
-      const double sigma_x = ss - tt;  // latent predictive variance (GPy predict, full_cov 1x1)
-      double outv;
-      if (a.mode == kModeVariance) {
-        outv = sigma_x;
-      } else {
-        const double v = xi - wk;            // _sampler.py:399
-        const double v2 = v * v;             // :401
-        const double kxx = sigma_x + noise;  // :397 predict(include_likelihood=True)
-        const double sigma2 = sigma1 - v2 / kxx;  // :400
-        double kld;
-        if (a.form == kFormLog1p) {
-          kld = -0.5 * log1p(-(v2 / (sigma1 * kxx)));
-        } else {
-          // :480, same operation order as the reference expression
-          kld = ((log(sqrt(sigma1) / sqrt(sigma2)) + (sigma2 / (2.0 * sigma1))) + ((v2 / sigma1) / (sigma_x + noise)) * 0.5) - 0.5;
-        }
-        outv = log(kld);  // :492 np.log(kld_j)
+      for (int j = 0; j < NRS; j++) wk += pvp[j * C + tid];
+#pragma unroll
+      if (!a.xi_ovr)
+#pragma unroll
+        for (int j = 0; j < NJQ; j++) xf *= xipp[j * C + tid];
+      if (c0 + tid < a.Nd) {
+        const size_t o = (size_t)(s_begin + ls) * a.Nd + c0 + tid;
+        const double xi = a.xi_ovr ? a.xi_ovr[o] : ss * xf;
+        a.logk[o] = ss - tt;                              // latent predictive variance (GPy predict, full_cov 1x1)
+        if (a.mode != kModeVariance) a.vplane[o] = xi - wk;  // _sampler.py:399
       }
-      if (c0 + tid < a.Nd) a.logk[(size_t)(s_begin + ls) * a.Nd + c0 + tid] = outv;
     }
+    TS_STAMP(7);
+#ifdef BODE_TIMELINE
+    if (ts_on && lane == 0 && ls < 16) { g_tw[((ts_item * 16 + warp) * 16 + ls) * 2] = tw_acc[0]; g_tw[((ts_item * 16 + warp) * 16 + ls) * 2 + 1] = tw_acc[1]; }
+#endif
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// K4: closed-form Gaussian EKLD of every (hyper-sample, candidate) from sigma_x and v, in place over the sigma_x plane
+// (avg_kld_mean, reference bode/_sampler.py:474-481, and the log of mcmc_kld :492)
+// ----------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ekld(const char* __restrict__ ws, Layout L, double* __restrict__ logk,
+                                              const double* __restrict__ vplane, int S, int64_t Nd, int form) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Nd) return;
+  for (int s = blockIdx.y; s < S; s += gridDim.y) {
+    const double* aux = reinterpret_cast<const double*>(ws + L.off_aux) + (size_t)s * L.aux_doubles;
+    const double noise = aux[C_NOISE], sigma1 = aux[C_SIGMA1];
+    const size_t o = (size_t)s * Nd + c;
+    const double sigma_x = logk[o];
+    const double v = vplane[o];          // _sampler.py:399
+    const double v2 = v * v;             // :401
+    const double kxx = sigma_x + noise;  // :397 predict(include_likelihood=True)
+    const double sigma2 = sigma1 - v2 / kxx;  // :400
+    double kld;
+    if (form == kFormLog1p) {
+      kld = -0.5 * log1p(-(v2 / (sigma1 * kxx)));
+    } else {
+      // :480, same operation order as the reference expression
+      kld = ((log(sqrt(sigma1) / sqrt(sigma2)) + (sigma2 / (2.0 * sigma1))) + ((v2 / sigma1) / (sigma_x + noise)) * 0.5) - 0.5;
+    }
+    logk[o] = log(kld);  // :492 np.log(kld_j)
   }
 }
 
@@ -541,7 +683,7 @@ __global__ void k_exp_inplace(double* __restrict__ v, size_t n) {
 // Host-side planning and launch
 // ----------------------------------------------------------------------------------------------------------------
 static size_t score_smem_bytes(const Layout& L, int C, int RG, int nthreads, int stages, int chunk_max, int nchunks, int u_global) {
-  size_t dbl = (size_t)L.npad * C + (u_global ? (size_t)aux_u(L) : L.aux_doubles) + (size_t)stages * chunk_max + (size_t)RG * C + 4 * (size_t)nthreads +
+  size_t dbl = (size_t)L.npad * C + (u_global ? (size_t)aux_nw() : L.aux_doubles) + (size_t)stages * chunk_max + (size_t)RG * C + 2 * (size_t)nthreads + (size_t)nthreads / 2 +
                (size_t)C * kXtStride;
   return dbl * sizeof(double) + sizeof(uint64_t) * (2 * kMaxStages + 1) +
          sizeof(int) * (2 * (nchunks + 2) + 8) + 128;
@@ -685,6 +827,13 @@ cudaError_t launch_score(const ScoreArgs& a, const ScorePlan& P, cudaStream_t st
   if (P.variant == 5) return launch_one<16, 1, 8, 1>(a, P, st);
   if (P.variant == 1) return launch_one<4, 4, 16, 1>(a, P, st);
   return launch_one<8, 2, 16, 1>(a, P, st);
+}
+
+cudaError_t launch_ekld(const void* ws, const Layout& L, double* logk, const double* vplane, int S, int64_t Nd, int form,
+                        cudaStream_t st) {
+  const dim3 grid((unsigned)((Nd + 255) / 256), (unsigned)(S < 65535 ? S : 65535));
+  k_ekld<<<grid, 256, 0, st>>>(static_cast<const char*>(ws), L, logk, vplane, S, Nd, form);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_reduce(const double* logk, int S, int64_t Nd, int64_t idx_offset, double* score, double* var,

@@ -24,7 +24,8 @@ struct ScoreArgs {
   Layout L;
   const double* Xd;  // Nd * d
   int64_t Nd;
-  double* logk;      // S * Nd
+  double* logk;      // S * Nd: sigma_x out of the scoring kernel, log EKLD after k_ekld
+  double* vplane;    // S * Nd: v = Cov(Q, f(x) | data) out of the scoring kernel (EKLD mode)
   const double* xi_ovr;  // S * Nd or null: quadrature estimate of xik(x) (k_rowmean); null = closed form (erf)
   int S;
   int sc;            // hyper-samples per work item
@@ -32,8 +33,7 @@ struct ScoreArgs {
   int form, mode;
   int debug_skip;    // developer timing knob (env BODE_DEBUG_SKIP): 1 = skip phase A after the first sample, 2 = skip phase B's DMMAs
   int stages, chunk_max /* doubles */, nchunks;
-  int epi_groups;    // phase-A groups the epilogue slice (threads < C) is relieved of (tuning knob, default 3)
-  int u_global;      // 1: the prescaled observations U stay in global memory (large n: they do not fit in smem)
+  int u_global;      // 1: the tiled observations Ut and the (nun, w) pairs stay in global memory (large n)
   unsigned short chunk_g0[kMaxChunks + 1];
   short tile_id[kMaxRG * kMaxRT];  // [rg][slot], right-aligned ascending, -1 = unused
 };

@@ -171,7 +171,7 @@ class EkldEngine:
             var = torch.empty(Nd, dtype=torch.float64, device=self.device) if want_var else None
             best = torch.empty(1, dtype=torch.float64, device=self.device)
             best_idx = torch.empty(1, dtype=torch.int64, device=self.device)
-            scr = self._buf("scratch", 256 + self.lib.bode_ekld_score_scratch_bytes(Nd), torch.uint8)
+            scr = self._buf("scratch", 256 + self.lib.bode_ekld_score_scratch_bytes(Nd, self.S), torch.uint8)
             args = [_ptr(self.ws), self.n, self.d, self.S, _ptr(Xd), Nd, int(idx_offset), int(form), _ptr(logk),
                     _ptr(score), _ptr(var), _ptr(best), _ptr(best_idx), _ptr(scr), self._stream()]
             if self.quad is not None:
@@ -205,7 +205,7 @@ class EkldEngine:
             pv = torch.empty(Ng, dtype=torch.float64, device=self.device)
             best = torch.empty(1, dtype=torch.float64, device=self.device)
             best_idx = torch.empty(1, dtype=torch.int64, device=self.device)
-            scr = self._buf("scratch", self.lib.bode_ekld_score_scratch_bytes(Ng), torch.uint8)
+            scr = self._buf("scratch", self.lib.bode_ekld_score_scratch_bytes(Ng, self.S), torch.uint8)
             _ext.check(self.lib.bode_us_variance_dev(_ptr(self.ws), self.n, self.d, self.S, _ptr(Xg), Ng, int(idx_offset),
                                                      _ptr(sigx), _ptr(pv), _ptr(best), _ptr(best_idx), _ptr(scr),
                                                      self._stream()))

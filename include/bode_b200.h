@@ -77,12 +77,13 @@ int bode_ekld_sample_terms_dev(const void* workspace, int n, int d, int S, doubl
 int bode_ekld_mu_sigma_dev(const void* workspace, int n, int d, int S, double* out, void* stream);
 
 /* K2+K3+K4 -- dense scoring; replaces Nd calls of mcmc_kld (`_sampler.py:483-492`):
- *   logk[s*Nd + c] = log EKLD_s(X_design[c])                    (always written; scratch of S*Nd doubles)
+ *   logk[s*Nd + c] = log EKLD_s(X_design[c])                    (always written; caller-provided S*Nd doubles)
  *   score[c] = (1/S) sum_s logk[s][c]  (sequential in s),  var[c] = (1/S) sum_s (logk[s][c]-score[c])^2 (nullable)
  *   best[0] = max score (NaN counts as largest, like np.argmax), best_idx[0] = idx_offset + first index attaining it.
  * `idx_offset` is the global index of X_design[0] (multi-GPU candidate sharding).
- * `scratch` needs bode_ekld_score_scratch_bytes(Nd) bytes. */
-size_t bode_ekld_score_scratch_bytes(int64_t Nd);
+ * `scratch` needs bode_ekld_score_scratch_bytes(Nd, S) bytes (argmax partials and the S*Nd plane of
+ * v = Cov(Q, f(x) | data) that the scoring kernel hands to the EKLD kernel). */
+size_t bode_ekld_score_scratch_bytes(int64_t Nd, int S);
 int bode_ekld_score_dev(const void* workspace, int n, int d, int S, const double* X_design, int64_t Nd,
                         int64_t idx_offset, int form, double* logk, double* score, double* var, double* best,
                         int64_t* best_idx, void* scratch, void* stream);
@@ -110,7 +111,7 @@ int bode_ekld_prepare_quad_dev(const double* X, const double* Y, const double* h
                                double nugget_var, double jitter, const double* Xq, const double* wq, int Nq,
                                void* workspace, size_t workspace_bytes, int* info, void* scratch, void* stream);
 /* bode_ekld_score_dev with xi_q(x) in place of xik(x); xi is an S*Nd scratch (returned filled);
- * scratch >= 256 + bode_ekld_score_scratch_bytes(Nd). */
+ * scratch >= 256 + bode_ekld_score_scratch_bytes(Nd, S). */
 int bode_ekld_score_quad_dev(const void* workspace, int n, int d, int S, const double* hyp, int ndim,
                              const double* X_design, int64_t Nd, int64_t idx_offset, int form, const double* Xq,
                              const double* wq, int Nq, double* xi, double* logk, double* score, double* var, double* best,

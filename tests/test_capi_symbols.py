@@ -41,7 +41,7 @@ def test_pure_host_entry_points(built_lib):
     assert 0 < w1 < w2 and w1 % 256 == 0
     assert lib.bode_ekld_workspace_bytes(2000, 8, 4) == 0
     assert lib.bode_ekld_workspace_bytes(10, 17, 4) == 0
-    assert lib.bode_ekld_score_scratch_bytes(100000) >= (100000 // 256) * 16
+    assert lib.bode_ekld_score_scratch_bytes(100000, 64) >= (100000 // 256) * 16 + 8 * 64 * 100000
     # argument validation happens before any CUDA call
     z = np.zeros(4)
     p = ctypes.c_void_p(z.ctypes.data)

@@ -313,24 +313,24 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "config3: d=8 n=200 S=64 |X_design|=1e5 per GPU (closed-form EKLD, dense scoring)",
-                       "step": "prepare (S Cholesky) + score all candidates + reduce over hyper-samples + argmax" +
+                       "step": "prepare (S Cholesky) + score all candidates (sigma_x, v) + EKLD + reduce over hyper-samples + argmax" +
                                (" + NCCL all_gather of (best, idx)" if world > 1 else ""),
                        "l2": "flushed between timed iterations (256 MB write)", "sharding": "candidate blocks, %d per rank" % Nd,
                        "wall_s_timed_region": wall},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak["dmma_tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / peak["dmma_tflops"], "traffic": 26968064,
-                         "traffic_unit": "bytes per launch (dram__bytes_read.sum 18.16 MB + dram__bytes_write.sum 8.80 MB; the 51 MB of "
-                                         "log-EKLD output mostly stays in the 126 MB L2 during the launch)",
-                         "traffic_source": "profiles/r1_k_score_bench_ncu_raw.txt: ncu --set full of this command, k_score launch",
+                         "frac": achieved / peak["dmma_tflops"], "traffic": 66353152,
+                         "traffic_unit": "bytes per launch (dram__bytes_read.sum 19.41 MB + dram__bytes_write.sum 46.94 MB; part of the 102 MB of "
+                                         "(sigma_x, v) output is still in the 126 MB L2 when the launch ends)",
+                         "traffic_source": "profiles/r1_v6_k_score_bench_ncu_raw.txt: ncu --set full of this command, k_score launch",
                          "kernel": "bode::k_score (FP64 tensor pipe, DMMA.8x8x4)", "kernel_ms": k_ms,
                          "flop_per_eval": F, "evals_per_launch": Nd * S,
                          "peak_source": "measured in this run: register-resident DMMA.8x8x4 loop (bode_fp64_peak); "
                                         "MEASURED_PEAKS.json has no FP64 entry",
                          "dfma_peak_tflops": peak["dfma_tflops"], "hbm_gbs_measured_peaks_json": peaks_file.get("hbm_gbs"),
-                         "algorithmic_bytes_per_eval": (8 * d + 8) / S + 8},
+                         "algorithmic_bytes_per_eval": (8 * d + 8) / S + 16},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": 4 * args.steps,
+            "gpu_launches": 5 * args.steps,  # k_prepare, k_score, k_ekld, k_reduce, k_final_argmax per step
             "clocks": clock_info,
             "best_idx": best[1],
         }

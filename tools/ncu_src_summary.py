@@ -27,18 +27,20 @@ if len(sys.argv) > 2:
         print("%s  samples=%s exec=%s  %s  | %s" % (r[ix["Address"]][-5:], r[ix["# Samples"]], r[ix["Instructions Executed"]],
               r[ix["Source"]].strip()[:70], ", ".join("%s=%d" % (c[6:], v) for v, c in st)))
 
-# ---- phase split relative to the DMMA region -------------------------------------------------------------------
-dm = [i for i, r in enumerate(body) if len(r) >= len(hdr) and 'DMMA' in r[ix['Source']]]
-if dm:
-    full = [r for r in body if len(r) >= len(hdr)]
-    dm = [i for i, r in enumerate(full) if 'DMMA' in r[ix['Source']]]
-    lo, hi = dm[0] - 60, dm[-1] + 40
-    stall_cols = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
-    def S(rs): return sum(int(float(r[ix['# Samples']] or 0)) for r in rs)
-    def I(rs): return sum(int(float(r[ix['Instructions Executed']] or 0)) for r in rs)
-    tot = S(full)
-    for name, rs in (('before-DMMA (phase A, setup, producer)', full[:lo]), ('DMMA region (phase B)', full[lo:hi]), ('after (reduce, epilogue)', full[hi:])):
-        d = {c: sum(int(float(r[ix[c]] or 0)) for r in rs) for c in stall_cols}
-        t = max(1, sum(d.values()))
-        print("%-40s samples %5.1f%%  inst %5.1f%%  top stalls: %s" % (name, 100.0 * S(rs) / tot, 100.0 * I(rs) / max(1, tot_inst),
-              ", ".join("%s %.0f%%" % (k[6:], 100.0 * v / t) for k, v in sorted(d.items(), key=lambda kv: -kv[1])[:5])))
+# ---- split at the CTA-wide barriers: (setup) | phase A ... BAR | phase B ... BAR | combine -----------------------------
+full = [r for r in body if len(r) >= len(hdr)]
+bars = [i for i, r in enumerate(full) if r[ix['Source']].strip().split()[0].startswith('BAR') or ' BAR.SYNC' in r[ix['Source']]]
+stall_cols = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
+def S(rs): return sum(int(float(r[ix['# Samples']] or 0)) for r in rs)
+def I(rs): return sum(int(float(r[ix['Instructions Executed']] or 0)) for r in rs)
+tot = max(1, S(full))
+cuts = [0] + [b + 1 for b in bars] + [len(full)]
+print("regions between CTA-wide barriers (SASS order): samples%, inst%, DMMA share of the region's instructions, top stalls")
+for lo, hi in zip(cuts, cuts[1:]):
+    rs = full[lo:hi]
+    if S(rs) < 0.005 * tot: continue
+    nd = sum(int(float(r[ix['Instructions Executed']] or 0)) for r in rs if 'DMMA' in r[ix['Source']])
+    d = {c: sum(int(float(r[ix[c]] or 0)) for r in rs) for c in stall_cols}
+    t = max(1, sum(d.values()))
+    print("  sass[%6d:%6d]  samples %5.1f%%  inst %5.1f%%  dmma/inst %4.1f%%  stalls: %s" % (lo, hi, 100.0 * S(rs) / tot, 100.0 * I(rs) / max(1, tot_inst),
+          100.0 * nd / max(1, I(rs)), ", ".join("%s %.0f%%" % (k[6:], 100.0 * v / t) for k, v in sorted(d.items(), key=lambda kv: -kv[1])[:5])))

@@ -330,7 +330,7 @@ struct PhaseB<RT, CT, RT> {
 };
 
 template <int RG, int CG, int RT, int CT>
-__global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && CT <= 2) ? 2 : 1) k_score(const __grid_constant__ ScoreArgs a) {
+__global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) ? 2 : 1) k_score(const __grid_constant__ ScoreArgs a) {
   constexpr int kWarps = RG * CG;        // 16: one CTA per SM (128 registers/thread)
   constexpr int kThreads = 32 * kWarps;
   constexpr int C = CG * CT * 8;         // candidates per CTA
@@ -776,20 +776,24 @@ static int plan_variant(const Layout& L, size_t smem_limit, ScorePlan* P) {
 
 int plan_score(const Layout& L, int64_t Nd, int sm_count, size_t smem_optin, ScorePlan* P) {
   const int nrt = L.nrt;
-  // BODE_SCORE_VARIANT=3|4 select experimental configurations for n <= 256 (tuning knob)
+  // BODE_SCORE_VARIANT=<id> forces one configuration (tuning knob); the default order is the measured
+  // preference: 8 warps with 32 accumulator tiles each (255 registers) beat 16 warps with 16 tiles (128 registers)
   const char* env = getenv("BODE_SCORE_VARIANT");
   const int forced = env ? atoi(env) : -1;
-  struct Cand { int variant, rg, cg, rt, ct; size_t limit; };
+  struct Cand { int variant, rg, cg, rt, ct; size_t limit; bool only_forced; };
   const Cand cands[] = {
-      {4, 4, 2, 8, 4, smem_optin}, {3, 4, 2, 8, 2, (228 * 1024) / 2 - 1024},  // only when forced
-      {0, 4, 4, 8, 2, smem_optin},    // n <= 256 : 64 candidates per CTA
-      {1, 4, 4, 16, 1, smem_optin},   // n <= 512 : 32 candidates per CTA
-      {2, 8, 2, 16, 1, smem_optin},   // n <= 1024: 16 candidates per CTA
-      {5, 16, 1, 8, 1, smem_optin},   // n <= 1024:  8 candidates per CTA (largest L^-1 chunks)
+      {3, 4, 2, 8, 2, (228 * 1024) / 2 - 1024, true},  // two CTAs per SM, 32 candidates each (slower: L^-1 is streamed twice)
+      {4, 4, 2, 8, 4, smem_optin, false},    // n <= 256 : 64 candidates per CTA,  8 warps x (8 x 4) tiles
+      {0, 4, 4, 8, 2, smem_optin, false},    // n <= 256 : 64 candidates per CTA, 16 warps x (8 x 2) tiles
+      {6, 4, 2, 16, 2, smem_optin, false},   // n <= 512 : 32 candidates per CTA,  8 warps x (16 x 2) tiles
+      {1, 4, 4, 16, 1, smem_optin, false},   // n <= 512 : 32 candidates per CTA, 16 warps x (16 x 1) tiles
+      {7, 8, 1, 16, 2, smem_optin, false},   // n <= 1024: 16 candidates per CTA,  8 warps x (16 x 2) tiles
+      {2, 8, 2, 16, 1, smem_optin, false},   // n <= 1024: 16 candidates per CTA, 16 warps x (16 x 1) tiles
+      {5, 16, 1, 8, 1, smem_optin, false},   // n <= 1024:  8 candidates per CTA (largest L^-1 chunks)
   };
   bool ok = false;
   for (const Cand& c : cands) {
-    if ((c.variant == 3 || c.variant == 4) && forced != c.variant) continue;
+    if (forced >= 0 ? (forced != c.variant) : c.only_forced) continue;
     if (nrt > c.rg * c.rt) continue;
     P->variant = c.variant; P->rg = c.rg; P->cg = c.cg; P->rt = c.rt; P->ct = c.ct;
     if (plan_variant(L, c.limit, P) == 0) { ok = true; break; }
@@ -800,7 +804,7 @@ int plan_score(const Layout& L, int64_t Nd, int sm_count, size_t smem_optin, Sco
   // work items: (tile, sample chunk); aim for >= 16 waves of CTAs, keep at least 4 samples per item when possible
   const int64_t ntiles = (Nd + C - 1) / C;
   int sc = L.S;
-  int waves = 40;
+  int waves = 80;
   if (const char* wv = getenv("BODE_WAVES")) waves = atoi(wv);  // tuning knob
   const int64_t target = (int64_t)waves * sm_count;
   while (sc > 4 && ntiles * ((L.S + sc - 1) / sc) < target) sc = (sc + 1) / 2;
@@ -825,6 +829,8 @@ cudaError_t launch_score(const ScoreArgs& a, const ScorePlan& P, cudaStream_t st
   if (P.variant == 0) return launch_one<4, 4, 8, 2>(a, P, st);
   if (P.variant == 3) return launch_one<4, 2, 8, 2>(a, P, st);
   if (P.variant == 4) return launch_one<4, 2, 8, 4>(a, P, st);
+  if (P.variant == 6) return launch_one<4, 2, 16, 2>(a, P, st);
+  if (P.variant == 7) return launch_one<8, 1, 16, 2>(a, P, st);
   if (P.variant == 5) return launch_one<16, 1, 8, 1>(a, P, st);
   if (P.variant == 1) return launch_one<4, 4, 16, 1>(a, P, st);
   return launch_one<8, 2, 16, 1>(a, P, st);

@@ -87,7 +87,7 @@ def test_launch_plans_are_consistent(built_lib, n):
     assert g0[0] == 0 and g0[-1] == 2 * nrt and all(b > a and b % 2 == 0 for a, b in zip(g0, g0[1:]))
     blocks = lambda a, b: sum(nrt - (g >> 1) for g in range(a, b)) * 32
     assert all(blocks(a, b) <= p["chunk_doubles"] for a, b in zip(g0, g0[1:]))
-    assert p["smem_bytes"] <= 232448 and p["stages"] >= 2 and p["threads"] == 512
+    assert p["smem_bytes"] <= 232448 and p["stages"] >= 2 and p["threads"] in (256, 512)
     assert p["candidates_per_cta"] == p["col_groups"] * p["col_tiles_per_warp"] * 8
     assert p["tiles"] == -(-Nd // p["candidates_per_cta"])
     assert p["items"] == p["tiles"] * -(-S // p["samples_per_item"])

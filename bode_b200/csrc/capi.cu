@@ -413,6 +413,8 @@ int bode_fp64_peak(double* dmma_tflops, double* dfma_tflops) {
 #ifdef BODE_TIMELINE
 #include <stdio.h>
 namespace bode { cudaError_t debug_copy_timeline(long long* host); cudaError_t debug_set_phase_a(int v); }
+namespace bode { cudaError_t debug_copy_prepare_timeline(long long* host); }
+extern "C" int bode_debug_prepare(long long* out) { cudaDeviceSynchronize(); return bode::debug_copy_prepare_timeline(out) == cudaSuccess ? 0 : -4; }
 extern "C" int bode_debug_phase_a(int v) { return bode::debug_set_phase_a(v) == cudaSuccess ? 0 : -4; }
 extern "C" int bode_debug_dump(const char* path) {
   static long long buf[8 * 16 * 16 * 14];

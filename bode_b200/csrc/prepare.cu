@@ -87,10 +87,19 @@ __device__ __forceinline__ void panel_trsm_row(double (&P)[kNB], const double* L
   }
 }
 
+#ifdef BODE_TIMELINE
+__device__ long long g_tp[64 * 8];
+#define TP(i) do { if (threadIdx.x == 0 && blockIdx.x < 64) g_tp[blockIdx.x * 8 + (i)] = clock64(); } while (0)
+cudaError_t debug_copy_prepare_timeline(long long* host) { return cudaMemcpyFromSymbol(host, g_tp, sizeof(g_tp)); }
+#else
+#define TP(i) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
   extern __shared__ __align__(16) double sm[];
   const int s = blockIdx.x, tid = threadIdx.x;
   const int n = a.n, d = a.d, npad = a.L.npad;
+  TP(0);
   double* Ljp = sm;                        // [npad][8] staged panel rows
   double* Ld = Ljp + (size_t)npad * kNB;   // [8][8] diagonal block
   double* rdiag = Ld + kNB * kNB;          // [8] reciprocals of the diagonal of Ld
@@ -195,6 +204,7 @@ __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
   }
   __syncthreads();
 
+  TP(1);
   // ---- phase 1: bordered left-looking Cholesky -----------------------------------------------------------------
   const int nrows = n + 2;
   int info = fail;  // -1: rejected hyper-parameters
@@ -268,6 +278,7 @@ __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
     __syncthreads();
   }
 
+  TP(2);
   double* cst = aux;  // consts
   if (info) {
     // failed factorisation: poison the sample (NaN propagates to every EKLD of this sample), zero the factors.
@@ -313,6 +324,7 @@ __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
 
   if (a.loglik_only) return;  // the MCMC likelihood path needs only consts[C_LOGLIK]
 
+  TP(3);
   // ---- w = L^-T a : blocked back-substitution, 8 unknowns per step ---------------------------------------------
   for (int j = tid; j < npad; j += kPrepThreads) vec[j] = (j < n) ? arow[j] : 0.0;
   __syncthreads();
@@ -344,6 +356,7 @@ __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
   }
   for (int j = tid; j < npad; j += kPrepThreads) aux[aux_nw() + 2 * j + 1] = (j < n) ? vec[j] : 0.0;
 
+  TP(4);
   // ---- phase 2: X = I L^-T  (row r of X = column r of L^-1), same panel machinery -------------------------------
   for (int j0 = 0; j0 < n; j0 += kNB) {
     const int nb = min(kNB, n - j0);
@@ -372,6 +385,7 @@ __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
     }
   }
   __syncthreads();
+  TP(5);
   // ---- re-tile: block (R, g) element (rr, kk) = M[8R+rr][4g+kk] = X[4g+kk][8R+rr] --------------------------------
   const int nrt = a.L.nrt, ng = a.L.ng;
   for (int g = 0; g < ng; g++) {
@@ -387,6 +401,7 @@ __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
       Mt[goff + (size_t)blk * 32 + rr * 4 + kk] = v;
     }
   }
+  TP(6);
 }
 
 size_t prepare_smem_bytes(const Layout& L) {

@@ -241,6 +241,8 @@ static int score_common(const void* workspace, int n, int d, int S, const double
   {
     const char* dbg = getenv("BODE_DEBUG_SKIP");
     a.debug_skip = dbg ? atoi(dbg) : 0;
+    const char* sg = getenv("BODE_STAGGER");
+    a.stagger = sg ? atoi(sg) : 0;
   }
   a.stages = P.stages; a.chunk_max = P.chunk_max; a.nchunks = P.nchunks; a.u_global = P.u_global;
   memcpy(a.chunk_g0, P.chunk_g0, sizeof(a.chunk_g0));

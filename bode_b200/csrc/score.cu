@@ -136,7 +136,8 @@ cudaError_t debug_copy_timeline(long long* host /* 8*16*16*10 */) {
 //   z[j][c] = -|U_j|^2 - |y_c|^2 + 2 U_j . y_c   (scaled coordinates of layout.h / rbf.h; DK DMMAs per 8 x 8 tile, the
 //             A fragments come pre-tiled from the prepare kernel, the B fragments live in registers for the sample)
 //   k[j][c] = variance * 2^(z/64)                 (9 FP64 operations, table lookups on bank-staggered copies)
-// Warp w owns column tile w % NCT and the row tiles R == w / NCT (mod NRS); partial w.k per candidate; the xik factors
+// The warps of a column group (the RG warps that later contract these columns) build its CT column tiles: warp rg owns
+// column tile rg % CT and the row tiles R == rg / CT (mod RG / CT); partial w.k per candidate; the xik factors
 // (closed form, 2d erf per candidate) are spread over all threads as (candidate, dimension slice).
 //
 // Kc block (g, column tile) holds the 4 x 8 values of k4 group g in B-fragment order for phase B: position
@@ -189,14 +190,13 @@ __device__ __forceinline__ void phase_a_batch(const double2* __restrict__ nw, co
   }
 }
 
-template <int DK, int C, int NT>
+template <int DK, int C, int RG, int CT>
 __device__ __forceinline__ void phase_a(const double* __restrict__ aux, const double* __restrict__ nwp, const double* __restrict__ Ut,
-                                        int nrt, int d, const double* __restrict__ xt, double* __restrict__ Kc,
-                                        double* __restrict__ pv, int tid DBG_PARAM) {
-  constexpr int NW = NT / 32, NCT = C / 8, NRS = NW / NCT;
-  static_assert(NW % NCT == 0, "warps must split evenly over the column tiles");
-  const int warp = tid >> 5, lane = tid & 31;
-  const int ctile = warp % NCT, rs = warp / NCT;
+                                        int nrt, const double* __restrict__ xt, double* __restrict__ Kc,
+                                        double* __restrict__ pv, int rg, int cg, int lane DBG_PARAM) {
+  constexpr int NCT = C / 8, NRS = RG / CT;
+  static_assert(RG % CT == 0, "the warps of a column group must split evenly over its column tiles");
+  const int ctile = cg * CT + rg % CT, rs = rg / CT;
   const int r = lane >> 2, q = lane & 3;
   const double* cks = aux + aux_cks();
   const double* tab_lane = aux + aux_tabr() + (lane & (kTabRep - 1));
@@ -247,14 +247,14 @@ __device__ __forceinline__ void phase_a(const double* __restrict__ aux, const do
 }
 
 // xik(x) = variance * prod_k sqrt(pi)/sqrt(2) * ell_k * (erf((1-x_k) ck) - erf((0-x_k) ck))  (reference _core.py:86-92):
-// thread (candidate c, slice jq) multiplies the factors of the dimensions k == jq (mod NJQ)
-template <int C, int NT>
+// thread tg of column group cg (candidate c, slice jq) multiplies the factors of the dimensions k == jq (mod NJQ)
+template <int C, int RG, int CT>
 __device__ __forceinline__ void xik_factors(const double* __restrict__ aux, int d, const double* __restrict__ xt,
-                                            double* __restrict__ xip, int tid) {
-  constexpr int NJQ = NT / C;
+                                            double* __restrict__ xip, int cg, int tg) {
+  constexpr int GC = CT * 8, NJQ = RG * 32 / GC;   // candidates and dimension slices of one column group
   const double* ck = aux + aux_ck();
   const double* ell = aux + aux_ell();
-  const int c = tid % C, jq = tid / C;
+  const int c = cg * GC + tg % GC, jq = tg / GC;
   double xf = 1.0;
   for (int k = jq; k < d; k += NJQ) {
     const double x = xt[k * C + c];
@@ -263,14 +263,14 @@ __device__ __forceinline__ void xik_factors(const double* __restrict__ aux, int 
   xip[jq * C + c] = xf;
 }
 
-template <int C, int NT>
-__device__ __forceinline__ void phase_a_dispatch(const double* aux, const double* nwp, const double* Ut, int nrt, int d, int dk,
-                                                 const double* xt, double* Kc, double* pv, int tid DBG_PARAM) {
+template <int C, int RG, int CT>
+__device__ __forceinline__ void phase_a_dispatch(const double* aux, const double* nwp, const double* Ut, int nrt, int dk,
+                                                 const double* xt, double* Kc, double* pv, int rg, int cg, int lane DBG_PARAM) {
   switch (dk) {
-    case 1: phase_a<1, C, NT>(aux, nwp, Ut, nrt, d, xt, Kc, pv, tid DBG_ARG); break;
-    case 2: phase_a<2, C, NT>(aux, nwp, Ut, nrt, d, xt, Kc, pv, tid DBG_ARG); break;
-    case 3: phase_a<3, C, NT>(aux, nwp, Ut, nrt, d, xt, Kc, pv, tid DBG_ARG); break;
-    default: phase_a<4, C, NT>(aux, nwp, Ut, nrt, d, xt, Kc, pv, tid DBG_ARG); break;
+    case 1: phase_a<1, C, RG, CT>(aux, nwp, Ut, nrt, xt, Kc, pv, rg, cg, lane DBG_ARG); break;
+    case 2: phase_a<2, C, RG, CT>(aux, nwp, Ut, nrt, xt, Kc, pv, rg, cg, lane DBG_ARG); break;
+    case 3: phase_a<3, C, RG, CT>(aux, nwp, Ut, nrt, xt, Kc, pv, rg, cg, lane DBG_ARG); break;
+    default: phase_a<4, C, RG, CT>(aux, nwp, Ut, nrt, xt, Kc, pv, rg, cg, lane DBG_ARG); break;
   }
 }
 
@@ -334,7 +334,9 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
   constexpr int kWarps = RG * CG;        // 16: one CTA per SM (128 registers/thread)
   constexpr int kThreads = 32 * kWarps;
   constexpr int C = CG * CT * 8;         // candidates per CTA
-  constexpr int NJQ = kThreads / C;
+  constexpr int GC = CT * 8;             // candidates per column group
+  constexpr int GT = RG * 32;            // threads per column group
+  constexpr int NJQ = GT / GC;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const Layout& L = a.L;
@@ -354,7 +356,9 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
   const uint32_t full0 = smem_u32(bars);                          // full[stages]: TMA completion per ring stage
   const uint32_t empty0 = full0 + 8 * kMaxStages;                 // empty[stages]: all warps are done with the stage
   const uint32_t aux_full = empty0 + 8 * kMaxStages;
-  int* chunk_off = reinterpret_cast<int*>(bars + 2 * kMaxStages + 1);  // [nchunks+1] offset (doubles) of chunk q inside M_s
+  const uint32_t stagger = aux_full + 8;                          // first phase A of the even column groups is done
+  int* aux_cnt = reinterpret_cast<int*>(bars + 2 * kMaxStages + 2);    // warps that finished phase A so far (all samples)
+  int* chunk_off = aux_cnt + 2;                                         // [nchunks+1] offset (doubles) of chunk q inside M_s
   int* chunk_p0 = chunk_off + nchunks + 1;                              // [nchunks+2] first group PAIR of chunk q
 
   // ---- work item ----
@@ -370,6 +374,8 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
       mbar_init(empty0 + 8 * i, kWarps);
     }
     mbar_init(aux_full, 1);
+    mbar_init(stagger, RG * ((CG + 1) / 2));
+    aux_cnt[0] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int q = tid; q <= nchunks; q += kThreads) {
@@ -411,10 +417,16 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
     }
   }
 
-  // warp w runs on SM sub-partition w % 4: each sub-partition hosts the four ROW groups of one column group, so its
-  // warps have different tile sets (their bookkeeping interleaves) while it still owns exactly 1/4 of the DMMAs.
-  const int rg = warp / CG, cg = warp % CG;
-  const int cbase = cg * CT * 8;
+  // Column groups are independent pipelines: the RG warps of group cg build their own columns of Kc (phase A),
+  // contract them (phase B) and synchronise only among themselves (named barrier 1 + cg); the groups share the L^-1
+  // ring, the aux block and the FP64 pipe.  Warp w runs on sub-partition w % 4, which hosts one row group of every
+  // column group, so the barrier bubbles of one group fill with the work of another (measured: -2.8 % at config 3
+  // against CTA-wide barriers).  Starting the odd groups one phase A late on purpose (BODE_STAGGER=1) does not pay:
+  // the two-stage ring lets a group lead by one chunk at most, and deeper rings cost more in chunk transitions.
+  const int rg = warp % RG, cg = warp / RG;
+  const int tg = rg * 32 + lane;  // thread index inside the column group
+  const int cbase = cg * GC;
+  auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + cg), "n"(GT) : "memory"); };
   int toff[RT], pend[RT];
 #pragma unroll
   for (int t = 0; t < RT; t++) {
@@ -429,7 +441,7 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
   int st = 0, it = 0;
   uint32_t ph = 0;
   // refills trail the consumer by `lag` chunks so that the duty warp rarely has to wait for slower warps
-  const int lag = (stages >= 4) ? 2 : 1;
+  const int lag = (CG == 1 && stages >= 4) ? 2 : 1;  // (the lagging groups hold the duty when CG > 1: no extra lag needed)
   // refill cursor: (sample, chunk) that goes into the stage released by chunk it-lag, i.e. chunk it-lag+stages
   int rf_ls = 0, rf_q = 0;
   for (int i = 0; i < stages; i++) if (++rf_q == nchunks) { rf_q = 0; rf_ls++; }
@@ -453,27 +465,34 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
 #ifdef BODE_TIMELINE
     long long* tsa = (ts_on && ls < 16) ? &g_ta[((ts_item * 16 + warp) * 16 + ls) * 4] : nullptr;
 #endif
+    if (CG > 1 && ls == 0 && (cg & 1) && a.stagger) mbar_wait(stagger, 0);  // opt-in: odd groups one phase A behind
     double ss = 0;
-    if (tid < C) ss = auxs[C_SS];
+    if (tg < GC) ss = auxs[C_SS];
     if (!((a.debug_skip & 1) && ls > 0)) {
       // two call sites so that the fragment loads stay address-space specific (LDS vs LDG) instead of generic
       if (a.u_global) {
         const double* ag = aux_g + (size_t)ls * L.aux_doubles;
-        phase_a_dispatch<C, kThreads>(auxs, ag + aux_nw(), ag + aux_ut_off, nrt, L.d, L.dk, xt, Kc, pvp, tid DBG_ARG);
+        phase_a_dispatch<C, RG, CT>(auxs, ag + aux_nw(), ag + aux_ut_off, nrt, L.dk, xt, Kc, pvp, rg, cg, lane DBG_ARG);
       } else {
-        phase_a_dispatch<C, kThreads>(auxs, auxs + aux_nw(), auxs + aux_ut_off, nrt, L.d, L.dk, xt, Kc, pvp, tid DBG_ARG);
+        phase_a_dispatch<C, RG, CT>(auxs, auxs + aux_nw(), auxs + aux_ut_off, nrt, L.dk, xt, Kc, pvp, rg, cg, lane DBG_ARG);
       }
       TS_STAMP(5);  // (developer timeline: slot 5 = cross-covariance done, overwritten by nothing else)
-      if (!a.xi_ovr) xik_factors<C, kThreads>(auxs, L.d, xt, xipp, tid);
+      if (!a.xi_ovr) xik_factors<C, RG, CT>(auxs, L.d, xt, xipp, cg, tg);
     }
     TS_STAMP(2);
-    __syncthreads();
-    TS_STAMP(3);
-    // every warp is done with the aux block: fetch the next sample's while phase B runs
-    if (tid == 0 && ls + 1 < nsamp) {
-      mbar_arrive_expect_tx(aux_full, aux_bytes);
-      bulk_copy_g2s(smem_u32(auxs), aux_g + (size_t)(ls + 1) * L.aux_doubles, aux_bytes, aux_full);
+    // This warp is done with the aux block.  The last warp of the CTA to get here fetches the next sample's block
+    // (the groups run out of step, so nobody waits for it: a counter in shared memory instead of a barrier).
+    __syncwarp();
+    if (elect_one()) {
+      if (CG > 1 && ls == 0 && !(cg & 1)) mbar_arrive(stagger);
+      const int done = atomicAdd(aux_cnt, 1) + 1;
+      if (done == kWarps * (ls + 1) && ls + 1 < nsamp) {
+        mbar_arrive_expect_tx(aux_full, aux_bytes);
+        bulk_copy_g2s(smem_u32(auxs), aux_g + (size_t)(ls + 1) * L.aux_doubles, aux_bytes, aux_full);
+      }
     }
+    group_sync();
+    TS_STAMP(3);
 
     // ---- phase B: T = L^-1 Kc on the FP64 tensor pipe ----
     double acc[RT][CT][2];
@@ -487,8 +506,13 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
     const double* kb = kc_lane;
     auto enter = [&]() {  // start chunk q+1 (ring stage st)
       ++q;
-      if (it >= lag && ((it - lag) & (kWarps - 1)) == warp) {
-        // refill duty for the stage released `lag` chunks ago (chunk it-lag -> chunk it-lag+stages)
+      // refill duty for the stage released `lag` chunks ago (chunk it-lag -> chunk it-lag+stages) rotates over the
+      // warps of the odd column groups: they run one phase A behind, leave every chunk last and so rarely wait for
+      // the stage's empty barrier, and the leading groups never block on a straggler
+      constexpr int kDutyWarps = (CG > 1) ? RG * (CG / 2) : kWarps;
+      const int dj = (it - lag) & (kDutyWarps - 1);
+      const int duty_warp = (CG > 1) ? ((2 * (dj / RG) + 1) * RG + dj % RG) : dj;
+      if (it >= lag && duty_warp == warp) {
         if (rf_ls < nsamp && !(a.debug_skip & 4) && elect_one()) {
           const int pst = (st >= lag) ? st - lag : st - lag + stages;
           TS_WAIT_BEGIN();
@@ -539,24 +563,25 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
         red[rg * C + cbase + ct * 8 + col0 + 2] = p1;
       }
     }
-    __syncthreads();
+    group_sync();
     TS_STAMP(6);
 
     // ---- per-candidate combine: sigma_x = ss - |L^-1 k|^2 and v = xi - w.k (the EKLD itself is evaluated by k_ekld) ----
-    if (tid < C) {
-      double tt = red[tid];
+    if (tg < GC) {
+      const int cc = cbase + tg;  // this group's candidates
+      double tt = red[cc];
 #pragma unroll
-      for (int r = 1; r < RG; r++) tt += red[r * C + tid];
-      constexpr int NRS = kWarps / (C / 8);
+      for (int r = 1; r < RG; r++) tt += red[r * C + cc];
+      constexpr int NRS = RG / CT;
       double wk = 0.0, xf = 1.0;
 #pragma unroll
-      for (int j = 0; j < NRS; j++) wk += pvp[j * C + tid];
+      for (int j = 0; j < NRS; j++) wk += pvp[j * C + cc];
       if (!a.xi_ovr) {
 #pragma unroll
-        for (int j = 0; j < NJQ; j++) xf *= xipp[j * C + tid];
+        for (int j = 0; j < NJQ; j++) xf *= xipp[j * C + cc];
       }
-      if (c0 + tid < a.Nd) {
-        const size_t o = (size_t)(s_begin + ls) * a.Nd + c0 + tid;
+      if (c0 + cc < a.Nd) {
+        const size_t o = (size_t)(s_begin + ls) * a.Nd + c0 + cc;
         const double xi = a.xi_ovr ? a.xi_ovr[o] : ss * xf;
         a.logk[o] = ss - tt;                              // latent predictive variance (GPy predict, full_cov 1x1)
         if (a.mode != kModeVariance) a.vplane[o] = xi - wk;  // _sampler.py:399
@@ -686,7 +711,7 @@ __global__ void k_exp_inplace(double* __restrict__ v, size_t n) {
 static size_t score_smem_bytes(const Layout& L, int C, int RG, int nthreads, int stages, int chunk_max, int nchunks, int u_global) {
   size_t dbl = (size_t)L.npad * C + (u_global ? (size_t)aux_nw() : L.aux_doubles) + (size_t)stages * chunk_max + (size_t)RG * C + 2 * (size_t)nthreads + (size_t)nthreads / 2 +
                (size_t)C * kXtStride;
-  return dbl * sizeof(double) + sizeof(uint64_t) * (2 * kMaxStages + 1) +
+  return dbl * sizeof(double) + sizeof(uint64_t) * (2 * kMaxStages + 3) +
          sizeof(int) * (2 * (nchunks + 2) + 8) + 128;
 }
 

@@ -318,10 +318,10 @@ def main():
                        "l2": "flushed between timed iterations (256 MB write)", "sharding": "candidate blocks, %d per rank" % Nd,
                        "wall_s_timed_region": wall},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak["dmma_tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / peak["dmma_tflops"], "traffic": 66353152,
-                         "traffic_unit": "bytes per launch (dram__bytes_read.sum 19.41 MB + dram__bytes_write.sum 46.94 MB; part of the 102 MB of "
+                         "frac": achieved / peak["dmma_tflops"], "traffic": 66451712,
+                         "traffic_unit": "bytes per launch (dram__bytes_read.sum 19.42 MB + dram__bytes_write.sum 47.03 MB; part of the 102 MB of "
                                          "(sigma_x, v) output is still in the 126 MB L2 when the launch ends)",
-                         "traffic_source": "profiles/r1_v6_k_score_bench_ncu_raw.txt: ncu --set full of this command, k_score launch",
+                         "traffic_source": "profiles/r1_v7_k_score_bench_ncu_raw.txt: ncu --set full of this command, k_score launch",
                          "kernel": "bode::k_score (FP64 tensor pipe, DMMA.8x8x4)", "kernel_ms": k_ms,
                          "flop_per_eval": F, "evals_per_launch": Nd * S,
                          "peak_source": "measured in this run: register-resident DMMA.8x8x4 loop (bode_fp64_peak); "

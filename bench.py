@@ -182,6 +182,8 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # keep stdout to the one JSON line: NCCL's version / debug banner goes to a per-process file instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/bode_nccl_debug.%h.%p")
         tdist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     w = WORKLOAD

@@ -3,17 +3,18 @@
 // Replaces N_d * S evaluations of avg_kld_mean (reference bode/_sampler.py:464-481) and of the helpers it calls
 // (get_params_2 :391-402, predict / kern.K inside GPy, xik _core.py:86-92), and the log / mean / var / argmax of
 // mcmc_kld + optimize (:492, :659).  Per (candidate x, hyper-sample s):
-//     k   = K_ARD-RBF(X, x; theta_s)            (K2, phase A: direct-difference distance + exp, never leaves smem)
+//     k   = K_ARD-RBF(X, x; theta_s)            (K2, phase A: GEMM-form distance on the tensor pipe + exp2, never leaves smem)
 //     xi  = xik(x)                               (K2, closed form, 2d erf)
 //     t   = L_s^-1 k ; sigma_x = ss - t.t        (K3, phase B: FP64 tensor-core DMMA.8x8x4 against the tiled L^-1)
 //     v   = xi - w_s.k                           (K3, folded into phase A)
 //     EKLD = log(sqrt(s1)/sqrt(s2)) + s2/(2 s1) + (v^2/s1/(sigma_x+noise))*0.5 - 0.5 ; logk = log(EKLD)   (K4)
 //
 // Work decomposition: one CTA = one work item = (tile of C candidates) x (chunk of SC hyper-samples).  Per sample the
-// CTA runs phase A (all 16 warps build Kc[npad][C] in shared memory: the distance part on the FP64 tensor pipe, the
+// CTA runs phase A (all warps build Kc[npad][C] in shared memory: the distance part on the FP64 tensor pipe, the
 // exponential on the FP64 pipe), phase B (each warp owns up to RT row tiles x CT column tiles of T = L^-1 Kc as DMMA
 // accumulators; L^-1 streams through a shared-memory ring filled with 1-D bulk copies (TMA, cp.async.bulk + mbarrier)
-// by a rotating duty warp), and a short combine that writes sigma_x and v.  k_ekld turns those into log EKLD (K4),
+// by a rotating duty warp), and a short combine that writes sigma_x and v.  The column groups of a CTA run these
+// phases as independent pipelines (their own named barrier).  k_ekld turns those into log EKLD (K4),
 // k_reduce sums over s sequentially (deterministic, independent of how candidates were tiled or sharded across GPUs)
 // and does the block argmax, k_final_argmax picks the winner.
 #include <cuda_runtime.h>
@@ -298,7 +299,7 @@ __device__ __forceinline__ void mma_pair(double (&acc)[RT][CT][2], const int (&t
 }
 
 // ----------------------------------------------------------------------------------------------------------------
-// The scoring kernel.  16 compute warps = RG row groups x CG column groups; each warp owns up to RT row tiles
+// The scoring kernel.  RG x CG warps = RG row groups x CG column groups; each warp owns up to RT row tiles
 // (8 rows of T each) x CT column tiles (8 candidates each) as DMMA accumulators.  C = CG*CT*8 candidates per CTA.
 // ----------------------------------------------------------------------------------------------------------------
 // Static recursion over the number of dead accumulator slots: slot t dies at pair pend[t]; while slots T0.. are
@@ -331,7 +332,7 @@ struct PhaseB<RT, CT, RT> {
 
 template <int RG, int CG, int RT, int CT>
 __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) ? 2 : 1) k_score(const __grid_constant__ ScoreArgs a) {
-  constexpr int kWarps = RG * CG;        // 16: one CTA per SM (128 registers/thread)
+  constexpr int kWarps = RG * CG;        // 8 (255 registers/thread) or 16 (128), one CTA per SM
   constexpr int kThreads = 32 * kWarps;
   constexpr int C = CG * CT * 8;         // candidates per CTA
   constexpr int GC = CT * 8;             // candidates per column group
@@ -398,10 +399,9 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
   const uint32_t aux_bytes = (uint32_t)(aux_smem_doubles * sizeof(double));
   const uint32_t ring_u32 = smem_u32(ring), chunk_bytes_max = (uint32_t)a.chunk_max * 8u;
 
-  // There is no producer warp (all 16 warps compute, 128 registers per thread).  Ring protocol per chunk `it`:
-  // every warp waits full[st] (polled one chunk ahead so the poll's latency hides under the DMMAs), computes, and
-  // arrives on empty[st] (fire and forget); the refill of the stage used by chunk it-1 is issued when chunk it is
-  // entered by warp (it-lag) % kWarps (lag = 2 chunks), by which time the other warps have released it.
+  // There is no producer warp (every warp computes).  Ring protocol per chunk `it`: every warp waits full[st],
+  // computes, and arrives on empty[st] (fire and forget); the refill of the stage used by chunk it-lag is issued when
+  // chunk it is entered, by the warp on refill duty (see `enter` below).
   auto issue_chunk = [&](int ls_, int q_, int st_) {
     const uint32_t bytes = (uint32_t)(chunk_off[q_ + 1] - chunk_off[q_]) * 8u;
     mbar_arrive_expect_tx(full0 + 8 * st_, bytes);

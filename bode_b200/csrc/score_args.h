@@ -7,14 +7,10 @@
 
 namespace bode {
 
-constexpr int kComputeWarps = 16;
-constexpr int kComputeThreads = kComputeWarps * 32;  // 512
-constexpr int kScoreThreads = kComputeThreads + 128;  // + one producer warpgroup (1 active warp)
 constexpr int kMaxStages = 8;
 constexpr int kMaxRT = 16;      // row tiles per warp row-group
 constexpr int kMaxRG = 16;      // row groups
 constexpr int kMaxChunks = 256;
-constexpr int kMaxProg = kMaxChunks + kMaxRT;  // phase-B program entries per row group
 constexpr int kXtStride = 16;   // BODE_MAX_D doubles per candidate row in shared memory
 constexpr int kModeEkld = 0, kModeVariance = 1;
 constexpr int kFormReference = 0, kFormLog1p = 1;

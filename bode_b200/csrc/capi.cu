@@ -21,8 +21,8 @@ cudaError_t launch_mu_sigma(const void* ws, const Layout& L, double* out, cudaSt
 cudaError_t launch_loglik_gather(const void* ws, const Layout& L, double* out, cudaStream_t st);
 int plan_score(const Layout& L, int64_t Nd, int sm_count, size_t smem_optin, ScorePlan* P);
 cudaError_t launch_score(const ScoreArgs& a, const ScorePlan& P, cudaStream_t st);
-cudaError_t launch_ekld(const void* ws, const Layout& L, double* logk, const double* vplane, int S, int64_t Nd, int form,
-                        cudaStream_t st);
+cudaError_t launch_ekld(const void* ws, const Layout& L, const double* Xd, const double* xi_ovr, double* logk,
+                        const double* wkplane, int S, int64_t Nd, int form, cudaStream_t st);
 cudaError_t launch_reduce(const double* logk, int S, int64_t Nd, int64_t idx_offset, double* score, double* var,
                           double* part_val, int64_t* part_idx, double* best, int64_t* best_idx, cudaStream_t st);
 cudaError_t launch_exp_inplace(double* v, size_t n, cudaStream_t st);
@@ -235,7 +235,7 @@ static int score_common(const void* workspace, int n, int d, int S, const double
   const Layout L = make_layout(n, d, S);
   if (plan_score(L, Nd, props.sm_count, props.smem_optin, &P) != 0) return BODE_ERR_UNSUPPORTED;
   ScoreArgs a;
-  a.ws = workspace; a.L = L; a.Xd = Xd; a.Nd = Nd; a.logk = logk; a.S = S; a.xi_ovr = xi_ovr;
+  a.ws = workspace; a.L = L; a.Xd = Xd; a.Nd = Nd; a.logk = logk; a.S = S;
   a.vplane = reinterpret_cast<double*>(static_cast<char*>(scratch) + score_partials_bytes(Nd));
   a.sc = P.sc; a.ntiles = P.ntiles; a.form = form; a.mode = mode;
   {
@@ -256,7 +256,7 @@ static int score_common(const void* workspace, int n, int d, int S, const double
   }
   BODE_CUDA(launch_score(a, P, st));
   if (kernel_ms) BODE_CUDA(cudaEventRecord(ev1, st));
-  if (mode == kModeEkld) BODE_CUDA(launch_ekld(workspace, L, logk, a.vplane, S, Nd, form, st));
+  if (mode == kModeEkld) BODE_CUDA(launch_ekld(workspace, L, Xd, xi_ovr, logk, a.vplane, S, Nd, form, st));
   const size_t nb = (size_t)((Nd + 255) / 256);
   double* part_val = static_cast<double*>(scratch);
   int64_t* part_idx = reinterpret_cast<int64_t*>(static_cast<char*>(scratch) + align_up(nb * sizeof(double), 256));

@@ -247,23 +247,6 @@ __device__ __forceinline__ void phase_a(const double* __restrict__ aux, const do
   TSA(2);
 }
 
-// xik(x) = variance * prod_k sqrt(pi)/sqrt(2) * ell_k * (erf((1-x_k) ck) - erf((0-x_k) ck))  (reference _core.py:86-92):
-// thread tg of column group cg (candidate c, slice jq) multiplies the factors of the dimensions k == jq (mod NJQ)
-template <int C, int RG, int CT>
-__device__ __forceinline__ void xik_factors(const double* __restrict__ aux, int d, const double* __restrict__ xt,
-                                            double* __restrict__ xip, int cg, int tg) {
-  constexpr int GC = CT * 8, NJQ = RG * 32 / GC;   // candidates and dimension slices of one column group
-  const double* ck = aux + aux_ck();
-  const double* ell = aux + aux_ell();
-  const int c = cg * GC + tg % GC, jq = tg / GC;
-  double xf = 1.0;
-  for (int k = jq; k < d; k += NJQ) {
-    const double x = xt[k * C + c];
-    xf *= 1.2533141373155001 * ell[k] * (erf((1.0 - x) * ck[k]) - erf((0.0 - x) * ck[k]));
-  }
-  xip[jq * C + c] = xf;
-}
-
 template <int C, int RG, int CT>
 __device__ __forceinline__ void phase_a_dispatch(const double* aux, const double* nwp, const double* Ut, int nrt, int dk,
                                                  const double* xt, double* Kc, double* pv, int rg, int cg, int lane DBG_PARAM) {
@@ -337,7 +320,6 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
   constexpr int C = CG * CT * 8;         // candidates per CTA
   constexpr int GC = CT * 8;             // candidates per column group
   constexpr int GT = RG * 32;            // threads per column group
-  constexpr int NJQ = GT / GC;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const Layout& L = a.L;
@@ -351,9 +333,9 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
   double* ring = auxs + aux_smem_doubles;                        // [stages][chunk_max]
   double* red = ring + (size_t)stages * a.chunk_max;             // [RG][C]
   double* pv = red + RG * C;                                     // [2][NRS][C]   (NRS*C = 8 * kWarps)
-  double* xip = pv + 2 * 8 * kWarps;                             // [2][NJQ][C]   (NJQ*C = kThreads)
-  double* xt = xip + 2 * kThreads;                               // [kXtStride][C]  candidate tile, dimension-major
-  uint64_t* bars = reinterpret_cast<uint64_t*>(xt + C * kXtStride);
+  double* xt = pv + 2 * 8 * kWarps;                              // [4 dk][C]  candidate tile, dimension-major
+  const int xt_rows = 4 * L.dk;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xt + C * xt_rows);
   const uint32_t full0 = smem_u32(bars);                          // full[stages]: TMA completion per ring stage
   const uint32_t empty0 = full0 + 8 * kMaxStages;                 // empty[stages]: all warps are done with the stage
   const uint32_t aux_full = empty0 + 8 * kMaxStages;
@@ -385,7 +367,7 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
   }
   if (tid == 0) chunk_p0[nchunks + 1] = 0x7fffffff;  // read-ahead slot
   // candidate tile -> smem, dimension-major (rows beyond Nd are filled with a harmless interior point)
-  for (int idx = tid; idx < C * kXtStride; idx += kThreads) {
+  for (int idx = tid; idx < C * xt_rows; idx += kThreads) {
     const int k = idx / C, c = idx - k * C;
     double v = 0.5;
     if (k < L.d && c0 + c < a.Nd) v = a.Xd[(c0 + c) * L.d + k];
@@ -458,7 +440,6 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
     TS_STAMP(0);
     const int par = ls & 1;
     double* pvp = pv + par * 8 * kWarps;
-    double* xipp = xip + par * kThreads;
     // ---- phase A ----
     mbar_wait(aux_full, (uint32_t)par);
     TS_STAMP(1);
@@ -476,8 +457,7 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
       } else {
         phase_a_dispatch<C, RG, CT>(auxs, auxs + aux_nw(), auxs + aux_ut_off, nrt, L.dk, xt, Kc, pvp, rg, cg, lane DBG_ARG);
       }
-      TS_STAMP(5);  // (developer timeline: slot 5 = cross-covariance done, overwritten by nothing else)
-      if (!a.xi_ovr) xik_factors<C, RG, CT>(auxs, L.d, xt, xipp, cg, tg);
+      TS_STAMP(5);  // (developer timeline: slot 5 = cross-covariance done)
     }
     TS_STAMP(2);
     // This warp is done with the aux block.  The last warp of the CTA to get here fetches the next sample's block
@@ -566,25 +546,20 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
     group_sync();
     TS_STAMP(6);
 
-    // ---- per-candidate combine: sigma_x = ss - |L^-1 k|^2 and v = xi - w.k (the EKLD itself is evaluated by k_ekld) ----
+    // ---- per-candidate combine: sigma_x = ss - |L^-1 k|^2 and w.k (xik and the EKLD itself are evaluated by k_ekld) ----
     if (tg < GC) {
       const int cc = cbase + tg;  // this group's candidates
       double tt = red[cc];
 #pragma unroll
       for (int r = 1; r < RG; r++) tt += red[r * C + cc];
       constexpr int NRS = RG / CT;
-      double wk = 0.0, xf = 1.0;
+      double wk = 0.0;
 #pragma unroll
       for (int j = 0; j < NRS; j++) wk += pvp[j * C + cc];
-      if (!a.xi_ovr) {
-#pragma unroll
-        for (int j = 0; j < NJQ; j++) xf *= xipp[j * C + cc];
-      }
       if (c0 + cc < a.Nd) {
         const size_t o = (size_t)(s_begin + ls) * a.Nd + c0 + cc;
-        const double xi = a.xi_ovr ? a.xi_ovr[o] : ss * xf;
-        a.logk[o] = ss - tt;                              // latent predictive variance (GPy predict, full_cov 1x1)
-        if (a.mode != kModeVariance) a.vplane[o] = xi - wk;  // _sampler.py:399
+        a.logk[o] = ss - tt;                            // latent predictive variance (GPy predict, full_cov 1x1)
+        if (a.mode != kModeVariance) a.vplane[o] = wk;  // w.k = e_k^T A^-1 k(X, x), the data term of v (_sampler.py:399)
       }
     }
     TS_STAMP(7);
@@ -595,19 +570,35 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
 }
 
 // ----------------------------------------------------------------------------------------------------------------
-// K4: closed-form Gaussian EKLD of every (hyper-sample, candidate) from sigma_x and v, in place over the sigma_x plane
-// (avg_kld_mean, reference bode/_sampler.py:474-481, and the log of mcmc_kld :492)
+// K4: xik(x), v and the closed-form Gaussian EKLD of every (hyper-sample, candidate), in place over the sigma_x plane
+// (xik reference bode/_core.py:86-92; get_params_2 _sampler.py:399; avg_kld_mean :474-481; the log of mcmc_kld :492)
 // ----------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_ekld(const char* __restrict__ ws, Layout L, double* __restrict__ logk,
-                                              const double* __restrict__ vplane, int S, int64_t Nd, int form) {
+__global__ void __launch_bounds__(256) k_ekld(const char* __restrict__ ws, Layout L, const double* __restrict__ Xd,
+                                              const double* __restrict__ xi_ovr, double* __restrict__ logk,
+                                              const double* __restrict__ wkplane, int S, int64_t Nd, int form) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= Nd) return;
+  const int d = L.d;
+  double x[kCkPad];
+  if (!xi_ovr)
+    for (int k = 0; k < d; k++) x[k] = Xd[c * d + k];
   for (int s = blockIdx.y; s < S; s += gridDim.y) {
     const double* aux = reinterpret_cast<const double*>(ws + L.off_aux) + (size_t)s * L.aux_doubles;
-    const double noise = aux[C_NOISE], sigma1 = aux[C_SIGMA1];
+    const double ss = aux[C_SS], noise = aux[C_NOISE], sigma1 = aux[C_SIGMA1];
     const size_t o = (size_t)s * Nd + c;
+    double xi;
+    if (xi_ovr) {
+      xi = xi_ovr[o];  // quadrature estimate (k_rowmean)
+    } else {
+      // _core.py:86-92: ss * prod_k sqrt(pi)/sqrt(2) * ell_k * (erf((1-x)/(sqrt2 ell)) - erf((0-x)/(sqrt2 ell))), k ascending
+      const double* ck = aux + aux_ck();
+      const double* ell = aux + aux_ell();
+      double xf = 1.0;
+      for (int k = 0; k < d; k++) xf *= 1.2533141373155001 * ell[k] * (erf((1.0 - x[k]) * ck[k]) - erf((0.0 - x[k]) * ck[k]));
+      xi = ss * xf;
+    }
     const double sigma_x = logk[o];
-    const double v = vplane[o];          // _sampler.py:399
+    const double v = xi - wkplane[o];    // _sampler.py:399
     const double v2 = v * v;             // :401
     const double kxx = sigma_x + noise;  // :397 predict(include_likelihood=True)
     const double sigma2 = sigma1 - v2 / kxx;  // :400
@@ -709,8 +700,8 @@ __global__ void k_exp_inplace(double* __restrict__ v, size_t n) {
 // Host-side planning and launch
 // ----------------------------------------------------------------------------------------------------------------
 static size_t score_smem_bytes(const Layout& L, int C, int RG, int nthreads, int stages, int chunk_max, int nchunks, int u_global) {
-  size_t dbl = (size_t)L.npad * C + (u_global ? (size_t)aux_nw() : L.aux_doubles) + (size_t)stages * chunk_max + (size_t)RG * C + 2 * (size_t)nthreads + (size_t)nthreads / 2 +
-               (size_t)C * kXtStride;
+  size_t dbl = (size_t)L.npad * C + (u_global ? (size_t)aux_nw() : L.aux_doubles) + (size_t)stages * chunk_max + (size_t)RG * C + (size_t)nthreads / 2 +
+               (size_t)C * 4 * L.dk;
   return dbl * sizeof(double) + sizeof(uint64_t) * (2 * kMaxStages + 3) +
          sizeof(int) * (2 * (nchunks + 2) + 8) + 128;
 }
@@ -758,11 +749,13 @@ static int plan_chunks(const Layout& L, size_t smem_limit, size_t chunk_max, Sco
   P->nchunks = nch;
   P->chunk_max = (int)chunk_max;
   const int nthreads = 32 * P->rg * P->cg;
-  int stages = kMaxStages, u_global = 0;
+  int max_stages = 2, u_global = 0;  // two stages measured best (deeper rings mean smaller chunks, more transitions)
+  if (const char* sg = getenv("BODE_STAGES")) max_stages = atoi(sg) < 2 ? 2 : (atoi(sg) > kMaxStages ? kMaxStages : atoi(sg));
+  int stages = max_stages;
   while (stages >= 2 && score_smem_bytes(L, C, P->rg, nthreads, stages, (int)chunk_max, nch, 0) > smem_limit) stages--;
   if (stages < 2) {  // large n: leave the prescaled observations in global memory (read through L1/L2 in phase A)
     u_global = 1;
-    stages = kMaxStages;
+    stages = max_stages;
     while (stages >= 2 && score_smem_bytes(L, C, P->rg, nthreads, stages, (int)chunk_max, nch, 1) > smem_limit) stages--;
     if (stages < 2) return -1;
   }
@@ -781,18 +774,32 @@ static int plan_variant(const Layout& L, size_t smem_limit, ScorePlan* P) {
     size_t cm = (size_t)atoi(ck) * 128;
     return plan_chunks(L, smem_limit, cm < pair0_doubles ? pair0_doubles : cm, P);
   }
-  // Every chunk transition costs each warp ~450 cycles of barrier bookkeeping, so prefer few large chunks (two 40 KB
-  // stages measured best at config 3); fall back to smaller chunks when shared memory is short or U must stay global.
-  const size_t sizes_kb[] = {40, 32, 24, 16};
+  // Every chunk transition costs each warp ~450 cycles of barrier bookkeeping and two ring stages measured best, so:
+  // the smallest number k of chunks whose balanced partition (minimal largest chunk, pairs of k4 groups as atoms)
+  // fits twice in shared memory; the observations stay in shared memory unless no k allows it (large n).
+  auto balanced_max = [&](int k) -> size_t {  // minimal largest chunk (doubles) of a split into <= k contiguous chunks
+    size_t lo = pair0_doubles, hi = L.m_doubles;
+    while (lo < hi) {
+      const size_t mid = (lo + hi) / 2;
+      int cnt = 1;
+      size_t acc = 0;
+      for (int p = 0; p < L.nrt; p++) {
+        const size_t ps = (size_t)(L.nrt - p) * 64;
+        if (acc + ps > mid) { cnt++; acc = 0; }
+        acc += ps;
+      }
+      if (cnt <= k) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+  };
   ScorePlan best = *P;
   bool have = false;
-  for (size_t kb : sizes_kb) {
-    size_t cm = kb * 128;
-    if (cm < pair0_doubles) cm = pair0_doubles;
+  const int kmax = L.nrt < kMaxChunks ? L.nrt : kMaxChunks;
+  for (int k = 1; k <= kmax; k++) {
     ScorePlan T = *P;
-    if (plan_chunks(L, smem_limit, cm, &T) != 0) continue;
+    if (plan_chunks(L, smem_limit, balanced_max(k), &T) != 0) continue;
     if (!have || (best.u_global && !T.u_global)) { best = T; have = true; }
-    if (!T.u_global) break;  // largest chunk size that keeps U in shared memory
+    if (!T.u_global) break;  // fewest chunks that keep the observations in shared memory
   }
   if (!have) return -1;
   *P = best;
@@ -861,10 +868,10 @@ cudaError_t launch_score(const ScoreArgs& a, const ScorePlan& P, cudaStream_t st
   return launch_one<8, 2, 16, 1>(a, P, st);
 }
 
-cudaError_t launch_ekld(const void* ws, const Layout& L, double* logk, const double* vplane, int S, int64_t Nd, int form,
-                        cudaStream_t st) {
+cudaError_t launch_ekld(const void* ws, const Layout& L, const double* Xd, const double* xi_ovr, double* logk,
+                        const double* wkplane, int S, int64_t Nd, int form, cudaStream_t st) {
   const dim3 grid((unsigned)((Nd + 255) / 256), (unsigned)(S < 65535 ? S : 65535));
-  k_ekld<<<grid, 256, 0, st>>>(static_cast<const char*>(ws), L, logk, vplane, S, Nd, form);
+  k_ekld<<<grid, 256, 0, st>>>(static_cast<const char*>(ws), L, Xd, xi_ovr, logk, wkplane, S, Nd, form);
   return cudaGetLastError();
 }
 

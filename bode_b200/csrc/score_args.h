@@ -11,7 +11,6 @@ constexpr int kMaxStages = 8;
 constexpr int kMaxRT = 16;      // row tiles per warp row-group
 constexpr int kMaxRG = 16;      // row groups
 constexpr int kMaxChunks = 256;
-constexpr int kXtStride = 16;   // BODE_MAX_D doubles per candidate row in shared memory
 constexpr int kModeEkld = 0, kModeVariance = 1;
 constexpr int kFormReference = 0, kFormLog1p = 1;
 
@@ -21,8 +20,7 @@ struct ScoreArgs {
   const double* Xd;  // Nd * d
   int64_t Nd;
   double* logk;      // S * Nd: sigma_x out of the scoring kernel, log EKLD after k_ekld
-  double* vplane;    // S * Nd: v = Cov(Q, f(x) | data) out of the scoring kernel (EKLD mode)
-  const double* xi_ovr;  // S * Nd or null: quadrature estimate of xik(x) (k_rowmean); null = closed form (erf)
+  double* vplane;    // S * Nd: w.k = e_k^T A^-1 k(X, x) out of the scoring kernel (EKLD mode); k_ekld forms v = xik(x) - w.k
   int S;
   int sc;            // hyper-samples per work item
   int ntiles;        // candidate tiles

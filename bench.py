@@ -315,15 +315,15 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "config3: d=8 n=200 S=64 |X_design|=1e5 per GPU (closed-form EKLD, dense scoring)",
-                       "step": "prepare (S Cholesky) + score all candidates (sigma_x, v) + EKLD + reduce over hyper-samples + argmax" +
+                       "step": "prepare (S Cholesky) + score all candidates (sigma_x, w.k) + xik/EKLD + reduce over hyper-samples + argmax" +
                                (" + NCCL all_gather of (best, idx)" if world > 1 else ""),
                        "l2": "flushed between timed iterations (256 MB write)", "sharding": "candidate blocks, %d per rank" % Nd,
                        "wall_s_timed_region": wall},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak["dmma_tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / peak["dmma_tflops"], "traffic": 66451712,
-                         "traffic_unit": "bytes per launch (dram__bytes_read.sum 19.42 MB + dram__bytes_write.sum 47.03 MB; part of the 102 MB of "
-                                         "(sigma_x, v) output is still in the 126 MB L2 when the launch ends)",
-                         "traffic_source": "profiles/r1_v7_k_score_bench_ncu_raw.txt: ncu --set full of this command, k_score launch",
+                         "frac": achieved / peak["dmma_tflops"], "traffic": 67346176,
+                         "traffic_unit": "bytes per launch (dram__bytes_read.sum 19.57 MB + dram__bytes_write.sum 47.77 MB; part of the 102 MB of "
+                                         "(sigma_x, w.k) output is still in the 126 MB L2 when the launch ends)",
+                         "traffic_source": "profiles/r1_v8_k_score_bench_ncu_raw.txt: ncu --set full of this command, k_score launch",
                          "kernel": "bode::k_score (FP64 tensor pipe, DMMA.8x8x4)", "kernel_ms": k_ms,
                          "flop_per_eval": F, "evals_per_launch": Nd * S,
                          "peak_source": "measured in this run: register-resident DMMA.8x8x4 loop (bode_fp64_peak); "

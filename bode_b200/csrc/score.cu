@@ -227,9 +227,16 @@ __device__ __forceinline__ void phase_a(const double* __restrict__ aux, const do
   constexpr int kstride = 2 * NCT * 32;
   // four row tiles (eight independent exponentials per thread) per step; measured on B200: 2, 3, 4 or 6 tiles per
   // step are within 0.6 % of each other, the loop is throughput-bound
+#ifndef BODE_PA_NB
+#define BODE_PA_NB 4
+#endif
+  constexpr int NB = BODE_PA_NB;
   int R = rs;
-  for (; R + 3 * NRS < nrt; R += 4 * NRS) phase_a_batch<DK, 4>(nw, ut_lane, R, NRS, r, yb, nyn, tab_lane, wk, kst, kstride DBG_ARG);
-  const int left = (R < nrt) ? (nrt - R + NRS - 1) / NRS : 0;
+  for (; R + (NB - 1) * NRS < nrt; R += NB * NRS) phase_a_batch<DK, NB>(nw, ut_lane, R, NRS, r, yb, nyn, tab_lane, wk, kst, kstride DBG_ARG);
+  int left = (R < nrt) ? (nrt - R + NRS - 1) / NRS : 0;
+  if (NB > 4) {
+    while (left >= 4) { phase_a_batch<DK, 4>(nw, ut_lane, R, NRS, r, yb, nyn, tab_lane, wk, kst, kstride DBG_ARG); R += 4 * NRS; left -= 4; }
+  }
   if (left == 3) phase_a_batch<DK, 3>(nw, ut_lane, R, NRS, r, yb, nyn, tab_lane, wk, kst, kstride DBG_ARG);
   else if (left == 2) phase_a_batch<DK, 2>(nw, ut_lane, R, NRS, r, yb, nyn, tab_lane, wk, kst, kstride DBG_ARG);
   else if (left == 1) phase_a_batch<DK, 1>(nw, ut_lane, R, NRS, r, yb, nyn, tab_lane, wk, kst, kstride DBG_ARG);

@@ -87,16 +87,22 @@ __device__ __forceinline__ double rbf_exp64(double z, const double* __restrict__
   return __hiloint2double(__double2hiint(res) + (e << 20), __double2loint(res));
 }
 
-// N independent evaluations written stage by stage (the N dependency chains interleave in the instruction stream)
+// N independent evaluations written stage by stage (the N dependency chains interleave in the instruction stream).
+// SMEM32: `tab` is a 32-bit shared-memory address (already offset by the lane's copy): the lookup address is two
+// integer operations, (k & 63) and one scaled add, instead of the four a generic pointer index compiles to.
 template <int N, int REP>
-__device__ __forceinline__ void rbf_exp64_n(const double* __restrict__ z, const double* __restrict__ tab, double* __restrict__ out) {
+__device__ __forceinline__ void rbf_exp64_n(const double* __restrict__ z, unsigned tab_smem, double* __restrict__ out) {
   const double SHIFT = 6755399441055744.0;
   double t[N], f[N], p[N], T[N];
   int k[N];
 #pragma unroll
   for (int i = 0; i < N; i++) t[i] = z[i] + SHIFT;
 #pragma unroll
-  for (int i = 0; i < N; i++) { k[i] = __double2loint(t[i]); T[i] = tab[(k[i] & (kExpTab64 - 1)) * REP]; }
+  for (int i = 0; i < N; i++) {
+    k[i] = __double2loint(t[i]);
+    const unsigned addr = tab_smem + ((unsigned)(k[i] & (kExpTab64 - 1)) * (unsigned)(REP * 8));
+    asm("ld.shared.f64 %0, [%1];" : "=d"(T[i]) : "r"(addr));
+  }
 #pragma unroll
   for (int i = 0; i < N; i++) t[i] = t[i] - SHIFT;
 #pragma unroll

@@ -148,7 +148,7 @@ cudaError_t debug_copy_timeline(long long* host /* 8*16*16*10 */) {
 template <int DK, int NB>
 __device__ __forceinline__ void phase_a_batch(const double2* __restrict__ nw, const double* __restrict__ ut_lane, int R, int rstride,
                                               int r, const double (&yb)[DK], const double (&nyn)[2],
-                                              const double* __restrict__ tab_lane, double (&wk)[2], double* __restrict__ kst,
+                                              unsigned tab_lane, double (&wk)[2], double* __restrict__ kst,
                                               int kstride DBG_PARAM) {
   double acc[NB][2], wv[NB], af[NB][DK];
 #pragma unroll
@@ -200,7 +200,7 @@ __device__ __forceinline__ void phase_a(const double* __restrict__ aux, const do
   const int ctile = cg * CT + rg % CT, rs = rg / CT;
   const int r = lane >> 2, q = lane & 3;
   const double* cks = aux + aux_cks();
-  const double* tab_lane = aux + aux_tabr() + (lane & (kTabRep - 1));
+  const unsigned tab_lane = smem_u32(aux + aux_tabr() + (lane & (kTabRep - 1)));  // the aux block is in shared memory
   // B fragments (dimension 4i + q of candidate 8 ctile + r), doubled scaled coordinates
   double yb[DK];
 #pragma unroll

@@ -5,11 +5,11 @@
 //                consts[8]  = {variance, noise_var, sigma0, sigma1, mu1, logdet, Y^T A^-1 Y, loglik}
 //                ck[16]     = 1/(sqrt(2) ell_k)            (zero padded; arguments of erf in xik)
 //                ell[16]    = ell_k                        (one padded)
-//                cks[16]    = 2 kappa min(ck, ck_max)      (zero padded; kappa^2 = 64/ln 2, see rbf.h)
+//                cks[16]    = 2 kappa ck                   (zero padded; kappa^2 = 64/ln 2, see rbf.h)
 //                tabr[64][16] = variance * 2^(j/64), each entry replicated 16 times so that lane l reads copy l & 15:
 //                               the per-lane table lookups of a warp never collide on a shared-memory bank
 //                nw[npad][2] = {-|U_j|^2, (A^-1 e)_j}      (zero padded)
-//                Ut[nrt][dk][32] = U = kappa min(ck, ck_max)[k] * (X[j][k] - 1/2) in mma.m8n8k4 A-fragment order:
+//                Ut[nrt][dk][32] = U = kappa ck[k] * (X[j][k] - 1/2) in mma.m8n8k4 A-fragment order:
 //                               entry lane = rr*4 + kk of block (R, i) is U[8R + rr][4i + kk]   (zero padded)
 //              so that the cross-covariance tile of 8 observations x 8 candidates is
 //                  z = -|U_j|^2 - |y|^2 + 2 U_j . y   (dk DMMAs, y = the candidate scaled like U),   k = tab-exp2(z / 64).

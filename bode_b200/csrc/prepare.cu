@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
   double* rdiag = Ld + kNB * kNB;          // [8] reciprocals of the diagonal of Ld
   double* red = rdiag + kNB;               // [8] reduction scratch
   double* ck = red + 8;                    // [16]
-  double* cku = ck + kCkPad;               // [16] kappa * min(ck, ck_max): scale of U (rbf.h)
+  double* cku = ck + kCkPad;               // [16] kappa * ck: scale of U (rbf.h)
   double* tab = cku + kCkPad;              // [64] variance * 2^(j/64)
   double* vec = tab + kTab64;              // [npad] back-substitution right-hand side
   __shared__ int fail;
@@ -124,13 +124,20 @@ __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
   if (tid < kCkPad) {
     const double c = (tid < d) ? 1.0 / (SQRT2 * h[1 + tid]) : 0.0;
     ck[tid] = c;
-    cku[tid] = kKappa * fmin(c, kCkMax);
+    cku[tid] = kKappa * c;
   }
   if (tid >= 32 && tid < 32 + kTab64) tab[tid - 32] = ss * exp2((double)(tid - 32) / 64.0);
   if (tid == 0) {
     // hyper-parameter sanity: the scoring kernel's exponent arithmetic assumes a sane variance scale
     int bad = !(ss > 9.5e-7 && ss < 1.0e6) || !(noise >= 0.0 && noise < 1.0e6);
-    for (int k = 0; k < d; k++) bad |= !(h[1 + k] > 1e-300 && h[1 + k] < 1e300);
+    // ... and that the scaled squared distances stay below 2^31 (rbf.h): sum_k kappa^2 / (2 ell_k^2) < 2e9, i.e.
+    // lengthscales of at least ~2e-4 of the unit box
+    double c2 = 0.0;
+    for (int k = 0; k < d; k++) {
+      bad |= !(h[1 + k] > 1e-300 && h[1 + k] < 1e300);
+      c2 += (kKappa * kKappa) / (2.0 * h[1 + k] * h[1 + k]);
+    }
+    bad |= !(c2 < 2.0e9);
     fail = bad ? -1 : 0;
   }
   __syncthreads();

@@ -60,11 +60,10 @@ __device__ __forceinline__ double sqdist(const double* __restrict__ uj, const do
 // exp(-r^2) = 2^(z/64) with z = -|u - y|^2 in the scaled coordinates.  k = rint(z) splits z = k + f, |f| <= 1/2
 // exactly (no Cody-Waite constants needed); 2^(f/64) - 1 is a degree-5 Taylor polynomial in f (truncation 3.5e-17
 // relative), the 64-entry table holds variance * 2^(j/64) and 2^(k>>6) goes into the exponent field: 9 FP64-pipe
-// operations, no branches.  Valid for z in (-2^31, ~0]; the result saturates at variance * 2^-1000 for z < -64000.
+// operations, no branches.  Valid for z in (-2^31, ~0] (the prepare kernel rejects hyper-parameters that could exceed it);
+// the result saturates at variance * 2^-1000 for z < -64000.
 constexpr int kExpTab64 = 64;
 constexpr double kKappa = 9.608979270291599;      // sqrt(64 / ln 2)
-constexpr double kCkMax = 707.10678118654755;      // 1/(sqrt2 * 1e-3): lengthscales below 1e-3 of the unit box are
-                                                   // evaluated as 1e-3 in the covariance (keeps |z| < 2^31)
 
 // REP = stride between consecutive table entries (1: plain table; 16: the bank-staggered copies of layout.h, with
 // `tab` already offset by the lane's copy index)

@@ -83,7 +83,8 @@ def test_t1_elementwise(ext, d, n, S, Nd, lo, hi):
     assert abs(r["sigma_Q"] - ref["sigma_Q"]) <= 1e-8 * abs(ref["sigma_Q"])
 
 
-@pytest.mark.parametrize("n,variant_note", [(257, "RT16/CT1, 4x4 warps"), (500, "config-4 shape"), (513, "8x2 warps"), (700, "8x2 warps")])
+@pytest.mark.parametrize("n,variant_note", [(257, "8 warps x (16 x 2) tiles"), (500, "config-4 shape"), (513, "16 candidates per CTA"),
+                                            (700, "16 candidates per CTA"), (1000, "8 candidates per CTA, 16 warps")])
 def test_large_n_variants(ext, n, variant_note):
     """n > 256 and n > 512 switch kernel template variants; same tolerance."""
     d, S, Nd = 10, 3, 150
@@ -94,6 +95,52 @@ def test_large_n_variants(ext, n, variant_note):
     assert_t2(r["kld"], ref["kld"], t["kld"])
     assert_argmax(r["argmax"], ref["score"])
     np.testing.assert_allclose(r["mu_Q"], ref["mu_Q"], rtol=1e-9)
+
+
+@pytest.mark.parametrize("variant,n", [(0, 200), (1, 300), (2, 600), (5, 600), (3, 64)])
+def test_forced_kernel_variants_agree(ext, variant, n, monkeypatch):
+    """The non-default launch configurations (16-warp variants, two CTAs per SM) stay correct: same EKLD as the
+    default configuration up to the order of the column sums (1e-12), same argmax."""
+    d, S, Nd = 7, 4, 300
+    X, Y, Xd, hyp = cases.make_problem(d, n, S, Nd, seed=900 + n, ell_lo=0.3, ell_hi=0.9)
+    base = gpu_score(ext, X, Y, hyp, Xd)
+    monkeypatch.setenv("BODE_SCORE_VARIANT", str(variant))
+    forced = gpu_score(ext, X, Y, hyp, Xd)
+    monkeypatch.delenv("BODE_SCORE_VARIANT")
+    assert (forced["info"] == 0).all()
+    np.testing.assert_allclose(forced["kld"], base["kld"], rtol=1e-9, atol=1e-15)
+    np.testing.assert_allclose(forced["score"], base["score"], rtol=0, atol=1e-9)
+    assert forced["argmax"] == base["argmax"]
+
+
+def test_tiny_lengthscale_is_finite_and_matches_oracle(ext):
+    """Lengthscales far below the design spacing: every cross-covariance underflows to (almost) zero on both sides,
+    nothing overflows or turns NaN; below ~2e-4 of the unit box the hyper-sample is rejected (info = -1)."""
+    X, Y, Xd, hyp = cases.make_problem(3, 12, 4, 200, seed=5, ell_lo=0.2, ell_hi=0.6)
+    hyp[1, 1] = 1e-3
+    hyp[2, 1:] = 2e-3
+    bad = hyp.copy()
+    bad[3, 2] = 1e-5
+    rb = ext.ekld_score_host(X, Y, bad, Xd, 1e-6, raise_not_pd=False)
+    assert rb["info"].tolist() == [0, 0, 0, -1] and np.isnan(rb["score"]).all()
+    r = gpu_score(ext, X, Y, hyp, Xd)
+    ref = orc.score(X, Y, Xd, hyp)
+    assert (r["info"] == 0).all() and np.isfinite(r["kld"]).all() and np.isfinite(r["score"]).all()
+    np.testing.assert_allclose(r["kld"], ref["kld"], rtol=1e-8, atol=1e-15)
+    assert_argmax(r["argmax"], ref["score"])
+
+
+def test_candidate_on_top_of_an_observation(ext):
+    """x == X_j: the expanded squared distance cancels to rounding (z ~ 0), sigma_x drops to the noise level and the
+    EKLD stays within the T2 bar."""
+    X, Y, Xd, hyp = cases.make_problem(4, 40, 6, 120, seed=17, ell_lo=0.2, ell_hi=0.8)
+    Xd[:40] = X
+    r = gpu_score(ext, X, Y, hyp, Xd)
+    ref = orc.score(X, Y, Xd, hyp)
+    t = truth.ekld_truth(X, Y, Xd, hyp)
+    assert (r["info"] == 0).all() and np.isfinite(r["kld"]).all()
+    assert_t2(r["kld"], ref["kld"], t["kld"])
+    assert_argmax(r["argmax"], ref["score"])
 
 
 def test_noisy_layout_d_plus_2(ext):

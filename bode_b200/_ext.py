@@ -21,7 +21,7 @@ BODE_MAX_D = 16
 EXPORTS = (
     "bode_version", "bode_strerror", "bode_last_cuda_error", "bode_ekld_workspace_bytes", "bode_ekld_prepare_dev",
     "bode_ekld_sample_terms_dev", "bode_ekld_mu_sigma_dev", "bode_ekld_score_scratch_bytes", "bode_ekld_score_dev",
-    "bode_ekld_score_dev_timed", "bode_us_variance_dev", "bode_quad_scratch_bytes", "bode_quad_rowmean_dev",
+    "bode_ekld_score_dev_timed", "bode_ekld_score_dev_events", "bode_us_variance_dev", "bode_quad_scratch_bytes", "bode_quad_rowmean_dev",
     "bode_ekld_prepare_quad_dev", "bode_ekld_score_quad_dev", "bode_ekld_score_host", "bode_gp_loglik_host", "bode_gp_loglik_dev", "bode_ekld_plan_describe", "bode_fp64_peak",
 )
 
@@ -68,6 +68,8 @@ def load():
                                         ctypes.c_int64, ctypes.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]
     lib.bode_ekld_score_dev_timed.restype = ctypes.c_int
     lib.bode_ekld_score_dev_timed.argtypes = list(lib.bode_ekld_score_dev.argtypes) + [c_dp]
+    lib.bode_ekld_score_dev_events.restype = ctypes.c_int
+    lib.bode_ekld_score_dev_events.argtypes = list(lib.bode_ekld_score_dev.argtypes) + [c_dp, c_dp]
     lib.bode_quad_scratch_bytes.restype = ctypes.c_size_t
     lib.bode_quad_scratch_bytes.argtypes = [ctypes.c_int] * 3
     lib.bode_quad_rowmean_dev.restype = ctypes.c_int

@@ -223,7 +223,8 @@ size_t bode_ekld_score_scratch_bytes(int64_t Nd, int S) {
 
 static int score_common(const void* workspace, int n, int d, int S, const double* Xd, int64_t Nd, int64_t idx_offset,
                         int form, int mode, const double* xi_ovr, double* logk, double* score, double* var, double* best,
-                        int64_t* best_idx, void* scratch, void* stream, float* kernel_ms) {
+                        int64_t* best_idx, void* scratch, void* stream, float* kernel_ms, void* ev_start = nullptr,
+                        void* ev_stop = nullptr) {
   if (!workspace || !Xd || !logk || !score || !best || !best_idx || !scratch || !shape_ok(n, d, S) || Nd < 1)
     return BODE_ERR_BAD_ARG;
   if (form != BODE_FORM_REFERENCE && form != BODE_FORM_LOG1P) return BODE_ERR_BAD_ARG;
@@ -254,7 +255,9 @@ static int score_common(const void* workspace, int n, int d, int S, const double
     BODE_CUDA(cudaEventCreate(&ev1));
     BODE_CUDA(cudaEventRecord(ev0, st));
   }
+  if (ev_start) BODE_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_start), st));
   BODE_CUDA(launch_score(a, P, st));
+  if (ev_stop) BODE_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_stop), st));
   if (kernel_ms) BODE_CUDA(cudaEventRecord(ev1, st));
   if (mode == kModeEkld) BODE_CUDA(launch_ekld(workspace, L, Xd, xi_ovr, logk, a.vplane, S, Nd, form, st));
   const size_t nb = (size_t)((Nd + 255) / 256);
@@ -283,6 +286,14 @@ int bode_ekld_score_dev_timed(const void* workspace, int n, int d, int S, const 
   if (!score_kernel_ms) return BODE_ERR_BAD_ARG;
   return score_common(workspace, n, d, S, X_design, Nd, idx_offset, form, kModeEkld, nullptr, logk, score, var, best, best_idx,
                       scratch, stream, score_kernel_ms);
+}
+
+int bode_ekld_score_dev_events(const void* workspace, int n, int d, int S, const double* X_design, int64_t Nd,
+                               int64_t idx_offset, int form, double* logk, double* score, double* var, double* best,
+                               int64_t* best_idx, void* scratch, void* stream, void* ev_start, void* ev_stop) {
+  if (!ev_start || !ev_stop) return BODE_ERR_BAD_ARG;
+  return score_common(workspace, n, d, S, X_design, Nd, idx_offset, form, kModeEkld, nullptr, logk, score, var, best, best_idx,
+                      scratch, stream, nullptr, ev_start, ev_stop);
 }
 
 int bode_ekld_score_quad_dev(const void* workspace, int n, int d, int S, const double* hyp, int ndim,

@@ -154,7 +154,7 @@ class EkldEngine:
         return mu, sg
 
     # ---- K2-K4 ---------------------------------------------------------------------------------------------
-    def score(self, X_design, idx_offset=0, form=_ext.BODE_FORM_REFERENCE, want_var=True, timed=False):
+    def score(self, X_design, idx_offset=0, form=_ext.BODE_FORM_REFERENCE, want_var=True, timed=False, events=None):
         """Score every row of X_design (device or host array).  Returns device tensors:
         dict(score (Nd,), var (Nd,)|None, logk (S, Nd), best (1,), best_idx (1,) int64)."""
         if not self._prepared:
@@ -183,7 +183,11 @@ class EkldEngine:
                                                              _ptr(best), _ptr(best_idx), _ptr(scr), self._stream()))
                 self._keep_x = Xd
                 return dict(score=score, var=var, logk=logk, best=best, best_idx=best_idx, xi=xi)
-            if timed:
+            if events is not None:
+                # (start, stop) torch.cuda.Event pair recorded around the scoring kernel, no synchronisation
+                _ext.check(self.lib.bode_ekld_score_dev_events(*args, ctypes.c_void_p(events[0].cuda_event),
+                                                               ctypes.c_void_p(events[1].cuda_event)))
+            elif timed:
                 ms = ctypes.c_float(0.0)
                 _ext.check(self.lib.bode_ekld_score_dev_timed(*args, ctypes.c_void_p(ctypes.addressof(ms))))
                 self.last_kernel_ms = ms.value

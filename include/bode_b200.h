@@ -97,6 +97,13 @@ int bode_ekld_score_dev_timed(const void* workspace, int n, int d, int S, const 
                               int64_t idx_offset, int form, double* logk, double* score, double* var, double* best,
                               int64_t* best_idx, void* scratch, void* stream, float* score_kernel_ms);
 
+/* Same as bode_ekld_score_dev, and records the caller's CUDA events (cudaEvent_t, created with timing enabled) on
+ * `stream` immediately before and after the fused K2-K3 scoring kernel, without synchronising: the caller reads
+ * cudaEventElapsedTime once its own timed region is over (bench.py's roofline figure). */
+int bode_ekld_score_dev_events(const void* workspace, int n, int d, int S, const double* X_design, int64_t Nd,
+                               int64_t idx_offset, int form, double* logk, double* score, double* var, double* best,
+                               int64_t* best_idx, void* scratch, void* stream, void* ev_start, void* ev_stop);
+
 /* ---- quadrature mode (north star: k(X_design, X_quad) / k(X, X_quad) averaged over quadrature points) ------------------
  * The reference integrates the kernel over [0,1]^d in closed form (xik / bk, `_core.py:86-101`); quadrature mode
  * replaces the three integrals by (weighted) means over user-supplied quadrature points X_quad[Nq*d] (the drivers'

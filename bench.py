@@ -182,9 +182,19 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # keep stdout to the one JSON line: NCCL's version / debug banner goes to a per-process file instead
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/bode_nccl_debug.%h.%p")
-        tdist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # keep stdout to the one JSON line: NCCL prints its version banner to stdout when the communicator is created,
+        # so file descriptor 1 points at stderr while that happens
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            tdist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            tdist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     w = WORKLOAD
     d, n, S, Nd = w["d"], w["n"], w["S"], w["Nd"]
@@ -328,10 +338,10 @@ def main():
                        "l2": "flushed between timed iterations (256 MB write)", "sharding": "candidate blocks, %d per rank" % Nd,
                        "wall_s_timed_region": wall},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak["dmma_tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / peak["dmma_tflops"], "traffic": 67346176,
-                         "traffic_unit": "bytes per launch (dram__bytes_read.sum 19.57 MB + dram__bytes_write.sum 47.77 MB; part of the 102 MB of "
+                         "frac": achieved / peak["dmma_tflops"], "traffic": 67031040,
+                         "traffic_unit": "bytes per launch (dram__bytes_read.sum 19.68 MB + dram__bytes_write.sum 47.36 MB; part of the 102 MB of "
                                          "(sigma_x, w.k) output is still in the 126 MB L2 when the launch ends)",
-                         "traffic_source": "profiles/r1_v8_k_score_bench_ncu_raw.txt: ncu --set full of this command, k_score launch",
+                         "traffic_source": "profiles/r1_final_k_score_bench_ncu_raw.txt: ncu --set full of this command, k_score launch",
                          "kernel": "bode::k_score (FP64 tensor pipe, DMMA.8x8x4)", "kernel_ms": k_ms,
                          "flop_per_eval": F, "evals_per_launch": Nd * S,
                          "peak_source": "measured in this run: register-resident DMMA.8x8x4 loop (bode_fp64_peak); "

@@ -227,6 +227,54 @@ struct Timer {
   float stop() { CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b)); float ms; CK(cudaEventElapsedTime(&ms, a, b)); return ms; }
 };
 
+
+// DADD / DMUL issue rate (are they full-rate like DFMA?) and an int-heavy mix like the table exp2 of phase A
+template <int OP, int NACC>
+__global__ void __launch_bounds__(256) k_dop(double* out, int iters, double x, double y, long long* cyc) {
+  double acc[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; i++) acc[i] = threadIdx.x * 1e-3 + i + 1.0;
+  long long t0 = clock64();
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < NACC; i++) {
+      if (OP == 0) acc[i] = __dadd_rn(acc[i], y);
+      else if (OP == 1) acc[i] = __dmul_rn(acc[i], x);
+      else { acc[i] = __dadd_rn(acc[i], y); acc[i] = __fma_rn(acc[i], x, y); }  // alternating DADD / DFMA
+    }
+  }
+  long long t1 = clock64();
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < NACC; i++) s += acc[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
+
+// NF DFMA + NI integer operations per accumulator per iteration (does integer work steal FP64 issue slots?)
+template <int NACC, int NI>
+__global__ void __launch_bounds__(256) k_dfma_int(double* out, int iters, double x, double y, long long* cyc) {
+  double acc[NACC];
+  int v[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; i++) { acc[i] = threadIdx.x * 1e-3 + i; v[i] = threadIdx.x + i; }
+  long long t0 = clock64();
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < NACC; i++) {
+      acc[i] = fma(acc[i], x, y);
+#pragma unroll
+      for (int j = 0; j < NI; j++) v[i] = (v[i] ^ (v[i] >> 3)) + it;   // 2-3 integer instructions
+    }
+  }
+  long long t1 = clock64();
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < NACC; i++) s += acc[i] + v[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
+
 int main(int argc, char** argv) {
   int dev = 0; CK(cudaSetDevice(dev));
   cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, dev));
@@ -255,6 +303,15 @@ int main(int argc, char** argv) {
   RUN("dfma_acc8_occ4x256", 2 * 8, IT, 4, 256, (k_dfma<8><<<grid, 256>>>(out, IT, 1.0000001, 1e-9, cyc)));
   RUN("dfma_acc16_occ2x256", 2 * 16, IT, 2, 256, (k_dfma<16><<<grid, 256>>>(out, IT, 1.0000001, 1e-9, cyc)));
   RUN("dfma_acc4_occ8x256", 2 * 4, IT, 8, 256, (k_dfma<4><<<grid, 256>>>(out, IT, 1.0000001, 1e-9, cyc)));
+  RUN("dadd_acc8_occ4x256", 1 * 8, IT, 4, 256, (k_dop<0, 8><<<grid, 256>>>(out, IT, 1.0000001, 1e-9, cyc)));
+  RUN("dmul_acc8_occ4x256", 1 * 8, IT, 4, 256, (k_dop<1, 8><<<grid, 256>>>(out, IT, 1.0000001, 1e-9, cyc)));
+  RUN("dadd_dfma_alt_acc8_occ4x256", 3 * 8, IT, 4, 256, (k_dop<2, 8><<<grid, 256>>>(out, IT, 1.0000001, 1e-9, cyc)));
+  RUN("dadd_acc8_occ1x256", 1 * 8, IT, 1, 256, (k_dop<0, 8><<<grid, 256>>>(out, IT, 1.0000001, 1e-9, cyc)));
+  RUN("dfma_acc8_occ1x256", 2 * 8, IT, 1, 256, (k_dfma<8><<<grid, 256>>>(out, IT, 1.0000001, 1e-9, cyc)));
+  RUN("dfma_int1_acc8_occ1x256", 2 * 8, IT, 1, 256, (k_dfma_int<8, 1><<<grid, 256>>>(out, IT, 1.0000001, 1e-9, cyc)));
+  RUN("dfma_int2_acc8_occ1x256", 2 * 8, IT, 1, 256, (k_dfma_int<8, 2><<<grid, 256>>>(out, IT, 1.0000001, 1e-9, cyc)));
+  RUN("dfma_int1_acc8_occ2x256", 2 * 8, IT, 2, 256, (k_dfma_int<8, 1><<<grid, 256>>>(out, IT, 1.0000001, 1e-9, cyc)));
+  RUN("dfma_int2_acc8_occ2x256", 2 * 8, IT, 2, 256, (k_dfma_int<8, 2><<<grid, 256>>>(out, IT, 1.0000001, 1e-9, cyc)));
   RUN("dmma_acc8_occ1x256", 16 * 8, IT, 1, 256, (k_dmma<8><<<grid, 256>>>(out, IT, 1.0000001, 1e-9, cyc)));
   RUN("dmma_acc8_occ2x256", 16 * 8, IT, 2, 256, (k_dmma<8><<<grid, 256>>>(out, IT, 1.0000001, 1e-9, cyc)));
   RUN("dmma_acc16_occ1x256", 16 * 16, IT, 1, 256, (k_dmma<16><<<grid, 256>>>(out, IT, 1.0000001, 1e-9, cyc)));

@@ -19,6 +19,11 @@
 //                Row tiles R < g/2 lie strictly above the diagonal and are not stored.
 //   Lw[s]    : (n+2) x npad row-major scratch: Cholesky factor rows 0..n-1, then a = L^-1 e and z = L^-1 Y.
 //   Xw[s]    : n x npad row-major scratch: M^T (row r = column r of L^-1).
+//   xc[s]    : per dimension k a block of kXcStride doubles: the even Chebyshev series of the xik factor
+//                F_k(x) = sqrt(pi/2) ell_k (erf((1-x) c_k) + erf(x c_k)) = a_0/2 + sum_j a_j T_j(w),  w = 2 (2x-1)^2 - 1
+//                (F_k is symmetric about x = 1/2): [n_terms, a_0/2, a_1, ..., a_(kXcMax-1)]; n_terms = 0 means the
+//                series did not converge within kXcMax terms (very short lengthscale) and the factor is evaluated
+//                with erf directly.
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
@@ -35,6 +40,9 @@ constexpr int kConsts = 8;
 constexpr int kCkPad = 16;
 constexpr int kTabPad = 32;   // table of rbf_exp (quadrature row means)
 constexpr int kTab64 = 64;    // table of rbf_exp64 (Gram matrix and cross-covariances)
+constexpr int kXcMax = 48;     // longest even Chebyshev series kept for an xik factor
+constexpr int kXcNodes = 64;   // Gauss-Chebyshev nodes the series is computed from
+constexpr int kXcStride = 50;  // doubles per (sample, dimension) block of the xc section
 constexpr int kTabRep = 16;   // bank-staggered copies of each table entry in the aux block
 enum ConstIdx { C_SS = 0, C_NOISE = 1, C_SIGMA0 = 2, C_SIGMA1 = 3, C_MU1 = 4, C_LOGDET = 5, C_QUAD = 6, C_LOGLIK = 7 };
 
@@ -48,7 +56,8 @@ struct Layout {
   size_t m_doubles;    // per sample
   size_t lw_doubles;   // per sample
   size_t xw_doubles;   // per sample
-  size_t off_aux, off_m, off_lw, off_xw, total_bytes;  // byte offsets of the four sections
+  size_t xc_doubles;   // per sample
+  size_t off_aux, off_m, off_lw, off_xw, off_xc, total_bytes;  // byte offsets of the five sections
 };
 
 BODE_HD size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -68,7 +77,9 @@ BODE_HD Layout make_layout(int n, int d, int S) {
   L.off_m = align_up(L.off_aux + sizeof(double) * L.aux_doubles * S, 256);
   L.off_lw = align_up(L.off_m + sizeof(double) * L.m_doubles * S, 256);
   L.off_xw = align_up(L.off_lw + sizeof(double) * L.lw_doubles * S, 256);
-  L.total_bytes = align_up(L.off_xw + sizeof(double) * L.xw_doubles * S, 256);
+  L.xc_doubles = (size_t)kCkPad * kXcStride;
+  L.off_xc = align_up(L.off_xw + sizeof(double) * L.xw_doubles * S, 256);
+  L.total_bytes = align_up(L.off_xc + sizeof(double) * L.xc_doubles * S, 256);
   return L;
 }
 

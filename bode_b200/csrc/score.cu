@@ -582,26 +582,51 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
 // ----------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_ekld(const char* __restrict__ ws, Layout L, const double* __restrict__ Xd,
                                               const double* __restrict__ xi_ovr, double* __restrict__ logk,
-                                              const double* __restrict__ wkplane, int S, int64_t Nd, int form) {
+                                              const double* __restrict__ wkplane, int S, int64_t Nd, int form, int use_series) {
+  __shared__ double xc[kCkPad * kXcStride];  // Chebyshev series of the xik factors of the current sample (layout.h)
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= Nd) return;
+  const bool active = c < Nd;
   const int d = L.d;
-  double x[kCkPad];
-  if (!xi_ovr)
-    for (int k = 0; k < d; k++) x[k] = Xd[c * d + k];
   for (int s = blockIdx.y; s < S; s += gridDim.y) {
     const double* aux = reinterpret_cast<const double*>(ws + L.off_aux) + (size_t)s * L.aux_doubles;
+    if (!xi_ovr) {
+      __syncthreads();
+      const double* src = reinterpret_cast<const double*>(ws + L.off_xc) + (size_t)s * L.xc_doubles;
+      for (int idx = threadIdx.x; idx < d * kXcStride; idx += blockDim.x) xc[idx] = src[idx];
+      __syncthreads();
+    }
+    if (!active) continue;
     const double ss = aux[C_SS], noise = aux[C_NOISE], sigma1 = aux[C_SIGMA1];
     const size_t o = (size_t)s * Nd + c;
     double xi;
     if (xi_ovr) {
       xi = xi_ovr[o];  // quadrature estimate (k_rowmean)
     } else {
-      // _core.py:86-92: ss * prod_k sqrt(pi)/sqrt(2) * ell_k * (erf((1-x)/(sqrt2 ell)) - erf((0-x)/(sqrt2 ell))), k ascending
+      // _core.py:86-92: ss * prod_k sqrt(pi)/sqrt(2) * ell_k * (erf((1-x)/(sqrt2 ell)) - erf((0-x)/(sqrt2 ell))), k ascending;
+      // each factor from its even Chebyshev series (Clenshaw), or from erf where the series did not converge
       const double* ck = aux + aux_ck();
       const double* ell = aux + aux_ell();
       double xf = 1.0;
-      for (int k = 0; k < d; k++) xf *= 1.2533141373155001 * ell[k] * (erf((1.0 - x[k]) * ck[k]) - erf((0.0 - x[k]) * ck[k]));
+      for (int k = 0; k < d; k++) {
+        const double* a = xc + k * kXcStride;
+        const int n = use_series ? (int)a[0] : 0;
+        const double x = Xd[c * d + k];
+        double fk;
+        if (n > 0) {
+          const double u = fma(2.0, x, -1.0);
+          const double w = fma(2.0 * u, u, -1.0), w2 = 2.0 * w;  // w = 2 u^2 - 1
+          double b1 = 0.0, b2 = 0.0;
+          for (int j = n - 1; j >= 1; j--) {
+            const double t = fma(w2, b1, a[1 + j]) - b2;
+            b2 = b1;
+            b1 = t;
+          }
+          fk = fma(w, b1, a[1]) - b2;
+        } else {
+          fk = 1.2533141373155001 * ell[k] * (erf((1.0 - x) * ck[k]) - erf((0.0 - x) * ck[k]));
+        }
+        xf *= fk;
+      }
       xi = ss * xf;
     }
     const double sigma_x = logk[o];
@@ -878,7 +903,9 @@ cudaError_t launch_score(const ScoreArgs& a, const ScorePlan& P, cudaStream_t st
 cudaError_t launch_ekld(const void* ws, const Layout& L, const double* Xd, const double* xi_ovr, double* logk,
                         const double* wkplane, int S, int64_t Nd, int form, cudaStream_t st) {
   const dim3 grid((unsigned)((Nd + 255) / 256), (unsigned)(S < 65535 ? S : 65535));
-  k_ekld<<<grid, 256, 0, st>>>(static_cast<const char*>(ws), L, Xd, xi_ovr, logk, wkplane, S, Nd, form);
+  const char* sv = getenv("BODE_XIK_SERIES");  // developer knob: 0 = evaluate every xik factor with erf
+  const int use_series = !(sv && atoi(sv) == 0);
+  k_ekld<<<grid, 256, 0, st>>>(static_cast<const char*>(ws), L, Xd, xi_ovr, logk, wkplane, S, Nd, form, use_series);
   return cudaGetLastError();
 }
 

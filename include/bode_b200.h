@@ -60,7 +60,8 @@ size_t bode_ekld_workspace_bytes(int n, int d, int S);
  * candidate-independent parts of get_sigma_1 / get_mu_1 (`:404-422`):
  *   A_s = K_ARD-RBF(X, X; theta_s) + (noise_var_s + jitter) I,  L_s = chol(A_s),  M_s = L_s^-1,
  *   e_s = xik(X),  sigma0_s = bk,  a = L^-1 e,  w_s = L^-T a,  sigma1_s = sigma0 - a.a,  mu1_s = (L^-1 Y).a,
- *   loglik_s = 0.5(-n log 2pi - logdet A_s - Y^T A_s^-1 Y)      (GPy log_marginal, `_sampler.py:232`).
+ *   loglik_s = 0.5(-n log 2pi - logdet A_s - Y^T A_s^-1 Y)      (GPy log_marginal, `_sampler.py:232`),
+ * plus the Chebyshev series of the d factors of xik(x; theta_s) (`_core.py:86-92`) that the scoring call evaluates.
  * X[n*d], Y[n], hyp[S*ndim], info[S] are device pointers.  info[s] = 0, or j+1 if pivot j of sample s was not
  * positive (LAPACK dpotrf convention), or -1 if theta_s is outside the supported range (variance in (9.5e-7, 1e6),
  * 0 <= noise_var < 1e6, finite positive lengthscales with sum_k 1/ell_k^2 < 4.3e7, i.e. no shorter than ~2e-4 of the

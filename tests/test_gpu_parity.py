@@ -143,6 +143,34 @@ def test_candidate_on_top_of_an_observation(ext):
     assert_argmax(r["argmax"], ref["score"])
 
 
+@pytest.mark.parametrize("d,n,lo,hi", [(8, 60, 0.05, 0.12), (6, 40, 0.05, 0.9), (2, 12, 0.012, 0.03)])
+def test_xik_series_matches_erf(ext, d, n, lo, hi, monkeypatch):
+    """xik(x) through the even Chebyshev series of its factors (prepared per hyper-sample) against the direct erf
+    evaluation (BODE_XIK_SERIES=0) on well-conditioned problems, down to very short lengthscales (the last case
+    falls back to erf by itself)."""
+    X, Y, Xd, hyp = cases.make_problem(d, n, 6, 400, seed=300 + d, ell_lo=lo, ell_hi=hi)
+    Xd[:3] = [[0.0] * d, [1.0] * d, [0.5] * d]   # the ends and the centre of the symmetric series
+    series = gpu_score(ext, X, Y, hyp, Xd)
+    monkeypatch.setenv("BODE_XIK_SERIES", "0")
+    direct = gpu_score(ext, X, Y, hyp, Xd)
+    monkeypatch.delenv("BODE_XIK_SERIES")
+    assert (series["info"] == 0).all()
+    np.testing.assert_allclose(series["kld"], direct["kld"], rtol=1e-10, atol=1e-15)
+    assert_argmax(series["argmax"], direct["score"])  # (equal up to ties at rounding level)
+
+
+def test_xik_series_long_lengthscales_against_truth(ext):
+    """Long lengthscales: v = xik(x) - w.k cancels to ~1e-8 of its terms, so 1e-16 in xik moves the EKLD by 1e-7 and the
+    two evaluation routes can only be compared through the long-double truth (T2)."""
+    X, Y, Xd, hyp = cases.make_problem(3, 20, 6, 300, seed=303, ell_lo=0.5, ell_hi=20.0)
+    r = gpu_score(ext, X, Y, hyp, Xd)
+    ref = orc.score(X, Y, Xd, hyp)
+    t = truth.ekld_truth(X, Y, Xd, hyp)
+    assert (r["info"] == 0).all()
+    assert_t2(r["kld"], ref["kld"], t["kld"])
+    assert_argmax(r["argmax"], ref["score"])
+
+
 def test_noisy_layout_d_plus_2(ext):
     """noisy=True rows carry the noise std in the last column (`_sampler.py:454-457`)."""
     X, Y, Xd, hyp = cases.make_problem(4, 30, 5, 400, seed=3, ell_lo=0.15, ell_hi=0.5, noisy=True)

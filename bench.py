@@ -338,8 +338,8 @@ def main():
                        "l2": "flushed between timed iterations (256 MB write)", "sharding": "candidate blocks, %d per rank" % Nd,
                        "wall_s_timed_region": wall},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak["dmma_tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / peak["dmma_tflops"], "traffic": 67031040,
-                         "traffic_unit": "bytes per launch (dram__bytes_read.sum 19.68 MB + dram__bytes_write.sum 47.36 MB; part of the 102 MB of "
+                         "frac": achieved / peak["dmma_tflops"], "traffic": 66816512,
+                         "traffic_unit": "bytes per launch (dram__bytes_read.sum 19.43 MB + dram__bytes_write.sum 47.39 MB; part of the 102 MB of "
                                          "(sigma_x, w.k) output is still in the 126 MB L2 when the launch ends)",
                          "traffic_source": "profiles/r1_final_k_score_bench_ncu_raw.txt: ncu --set full of this command, k_score launch",
                          "kernel": "bode::k_score (FP64 tensor pipe, DMMA.8x8x4)", "kernel_ms": k_ms,
@@ -350,7 +350,7 @@ def main():
                          "algorithmic_bytes_per_eval": (8 * d + 8) / S + 16},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": 5 * args.steps,  # k_prepare, k_score, k_ekld, k_reduce, k_final_argmax per step
+            "gpu_launches": 6 * args.steps,  # k_prepare, k_xik_coef, k_score, k_ekld, k_reduce, k_final_argmax per step
             "clocks": clock_info,
             "best_idx": best[1],
         }

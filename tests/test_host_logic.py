@@ -122,3 +122,41 @@ def test_combine_argmax_semantics():
             j = int(np.argmax(x[lo:hi]))
             vals.append(x[lo + j]); idxs.append(lo + j)
         assert dist.combine_argmax(*t(vals, idxs))[1] == int(np.argmax(x))
+
+
+def test_xik_factor_chebyshev_series_method():
+    """The numerical method behind k_xik_coef / k_ekld, restated in NumPy: the xik factor
+    F(x) = sqrt(pi/2) ell (erf((1-x)c) + erf(xc)) is even about x = 1/2, so it is a series in T_j(2(2x-1)^2 - 1) computed
+    from 64 Gauss-Chebyshev nodes and cut at its rounding floor; the cut series reproduces F to ~1e-15 with a handful of
+    terms, and very short lengthscales are detected as not converged (erf path)."""
+    from scipy.special import erf
+    M, KMAX = 64, 48
+    i = np.arange(M)
+    theta = np.pi * (i + 0.5) / M
+    xn = 0.5 * (np.cos(theta / 2) + 1.0)
+    r = (np.arange(M)[:, None] * (2 * i[None, :] + 1)) % (4 * M)
+    cosr = np.cos(np.pi * r / (2 * M))          # exactly reduced argument, as the kernel does with cospi
+    rng = np.random.default_rng(3)
+    x = np.concatenate([[0.0, 1.0, 0.5], rng.random(20000)])
+    w = 2.0 * (2.0 * x - 1.0) ** 2 - 1.0
+    terms = {}
+    for ell in (0.05, 0.1, 0.3, 1.0, 5.0, 50.0):
+        c = 1.0 / (np.sqrt(2.0) * ell)
+        F = lambda t: 1.2533141373155001 * ell * (erf((1.0 - t) * c) - erf((0.0 - t) * c))
+        a = (2.0 / M) * (F(xn)[None, :] * cosr).sum(1)
+        big = np.nonzero(np.abs(a) > 4e-16 * abs(a[0]))[0]
+        assert big.max() < KMAX, "series must converge within 48 terms for ell >= 0.05"
+        n = int(big.max()) + 1
+        terms[ell] = n
+        b1 = np.zeros_like(w); b2 = np.zeros_like(w)
+        for j in range(n - 1, 0, -1):
+            b1, b2 = a[j] + 2.0 * w * b1 - b2, b1
+        got = 0.5 * a[0] + w * b1 - b2
+        rel = np.abs(got - F(x)) / F(x)
+        assert np.percentile(rel, 99) <= 2e-15 and rel.max() <= 1e-14, (ell, rel.max())
+    assert terms[5.0] <= 6 and terms[0.3] <= 14 and terms[0.05] <= 36 and terms[50.0] <= 3
+    # a lengthscale far below the node spacing near the ends does not converge -> the kernel falls back to erf
+    ell = 2e-3
+    c = 1.0 / (np.sqrt(2.0) * ell)
+    a = (2.0 / M) * ((1.2533141373155001 * ell * (erf((1.0 - xn) * c) - erf((0.0 - xn) * c)))[None, :] * cosr).sum(1)
+    assert (np.abs(a[KMAX:]) > 4e-16 * abs(a[0])).any()

@@ -56,6 +56,31 @@ def test_config1_samp_ex1_dense(ext, golden_dir):
     assert (r["info"] == 0).all() and not np.isnan(r["score"]).any()
 
 
+# ---- vectors produced by the reference's own code (tests/golden/ekld_ref_*.npz, generator tests/golden/make_golden.py) ----
+@pytest.mark.parametrize("tag,min_trusted", [("c1", 0.0), ("c2", 0.0), ("c3s", 1.0), ("noisy", 1.0)])
+def test_reference_code_vectors_on_gpu(ext, golden_dir, tag, min_trusted):
+    """The CUDA path against what the reference's unmodified `_sampler.py:391-492` returned (run over the GPy stand-in)
+    for config 1 (fixture hyper-samples, 1000 designs), a config-2 shape, a config-3 shape and the noisy layout."""
+    g = np.load(os.path.join(golden_dir, "ekld_ref_%s.npz" % tag))
+    X, Y, hyp, Xd, nugget = g["X"], g["Y"], g["hyp"], g["Xd"], float(g["nugget"])
+    r = gpu_score(ext, X, Y, hyp, Xd, nugget=nugget)
+    assert (r["info"] == 0).all()
+    t = truth.ekld_truth(X, Y, Xd, hyp, nugget=nugget)
+    trusted = assert_parity(r["kld"], g["kld"], t["kld"], min_trusted=min_trusted, what="CUDA vs reference code")
+    # per-sample scalars of get_sigma_1 / get_mu_1 (well-conditioned cases: 1e-9; otherwise against the truth)
+    if trusted.all():
+        assert_score(r["score"], g["mcmc_mean"], g["kld"])
+        np.testing.assert_allclose(r["var"], g["mcmc_var"], rtol=1e-6, atol=1e-9)
+        assert r["argmax"] == int(np.argmax(g["mcmc_mean"]))          # the reference's own chosen design
+        assert abs(r["mu_Q"] - g["mu_1"].mean()) <= 1e-10 * abs(g["mu_1"].mean()) + 1e-13
+        assert abs(r["sigma_Q"] - g["sigma_1"].mean()) <= 1e-8 * abs(g["sigma_1"].mean())
+    else:
+        tsc = np.log(t["kld"]).mean(0)
+        assert (np.abs(r["score"] - tsc) <= 2.0 * np.mean(1e-6 + 1e-15 / t["kld"], axis=0)).all()
+        assert_argmax(r["argmax"], tsc, tol=1e-6)
+        assert_argmax(int(np.argmax(g["mcmc_mean"])), tsc, tol=1e-6)   # ... and the reference's choice is in the same tie set
+
+
 # ---- T1: well-conditioned families, element-wise 1e-9 -------------------------------------------------------------
 @pytest.mark.parametrize("d,n,S,Nd,lo,hi", [
     (3, 24, 6, 500, 0.08, 0.25),

@@ -23,6 +23,9 @@ EXPORTS = (
     "bode_ekld_sample_terms_dev", "bode_ekld_mu_sigma_dev", "bode_ekld_score_scratch_bytes", "bode_ekld_score_dev",
     "bode_ekld_score_dev_timed", "bode_ekld_score_dev_events", "bode_us_variance_dev", "bode_quad_scratch_bytes", "bode_quad_rowmean_dev",
     "bode_ekld_prepare_quad_dev", "bode_ekld_score_quad_dev", "bode_ekld_score_host", "bode_gp_loglik_host", "bode_gp_loglik_dev", "bode_ekld_plan_describe", "bode_fp64_peak",
+    "bode_tuning_reload", "bode_ctx_create", "bode_ctx_destroy", "bode_ctx_alloc_count", "bode_ekld_score_host_ctx", "bode_gp_loglik_host_ctx",
+    "bode_nccl_unique_id", "bode_nccl_comm_create", "bode_nccl_comm_destroy", "bode_ekld_argmax_nccl", "bode_argmax_combine",
+    "bode_ekld_prepare_jitter_dev",
 )
 
 
@@ -57,6 +60,9 @@ def load():
     lib.bode_ekld_prepare_dev.restype = ctypes.c_int
     lib.bode_ekld_prepare_dev.argtypes = [c_dp, c_dp, c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                           ctypes.c_double, ctypes.c_double, c_dp, ctypes.c_size_t, c_dp, c_dp]
+    lib.bode_ekld_prepare_jitter_dev.restype = ctypes.c_int
+    lib.bode_ekld_prepare_jitter_dev.argtypes = [c_dp, c_dp, c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.c_double, c_dp, c_dp, ctypes.c_size_t, c_dp, c_dp]
     lib.bode_ekld_sample_terms_dev.restype = ctypes.c_int
     lib.bode_ekld_sample_terms_dev.argtypes = [c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_dp, c_dp]
     lib.bode_ekld_mu_sigma_dev.restype = ctypes.c_int
@@ -101,6 +107,28 @@ def load():
                                             ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t]
     lib.bode_fp64_peak.restype = ctypes.c_int
     lib.bode_fp64_peak.argtypes = [c_dp, c_dp]
+    lib.bode_tuning_reload.restype = ctypes.c_int
+    lib.bode_tuning_reload.argtypes = []
+    lib.bode_ctx_create.restype = ctypes.c_int
+    lib.bode_ctx_create.argtypes = [ctypes.POINTER(ctypes.c_void_p)]
+    lib.bode_ctx_destroy.restype = ctypes.c_int
+    lib.bode_ctx_destroy.argtypes = [c_dp]
+    lib.bode_ctx_alloc_count.restype = ctypes.c_longlong
+    lib.bode_ctx_alloc_count.argtypes = [c_dp]
+    lib.bode_ekld_score_host_ctx.restype = ctypes.c_int
+    lib.bode_ekld_score_host_ctx.argtypes = [c_dp] + list(lib.bode_ekld_score_host.argtypes)
+    lib.bode_gp_loglik_host_ctx.restype = ctypes.c_int
+    lib.bode_gp_loglik_host_ctx.argtypes = [c_dp] + list(lib.bode_gp_loglik_host.argtypes)
+    lib.bode_nccl_unique_id.restype = ctypes.c_int
+    lib.bode_nccl_unique_id.argtypes = [c_dp]
+    lib.bode_nccl_comm_create.restype = ctypes.c_int
+    lib.bode_nccl_comm_create.argtypes = [c_dp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+    lib.bode_nccl_comm_destroy.restype = ctypes.c_int
+    lib.bode_nccl_comm_destroy.argtypes = [c_dp]
+    lib.bode_ekld_argmax_nccl.restype = ctypes.c_int
+    lib.bode_ekld_argmax_nccl.argtypes = [c_dp, c_dp, c_dp, c_dp]
+    lib.bode_argmax_combine.restype = ctypes.c_int
+    lib.bode_argmax_combine.argtypes = [c_dp, ctypes.c_int, c_dp, c_dp]
     _lib = lib
     return lib
 
@@ -109,7 +137,7 @@ def check(status):
     if status != 0:
         lib = load()
         detail = lib.bode_strerror(status).decode()
-        if status == -4:
+        if status in (-4, -6):
             detail += " (" + lib.bode_last_cuda_error().decode() + ")"
         raise BodeError(status, detail)
 
@@ -125,8 +153,51 @@ def _f64(a, shape=None):
     return a
 
 
+def reload_tuning():
+    """Re-read the BODE_* tuning environment variables (they are otherwise read once, when the library is loaded)."""
+    check(load().bode_tuning_reload())
+
+
+class HostContext(object):
+    """Explicit reusable context for the host-buffer entry points (``bode_ctx_create`` / ``bode_ctx_destroy``)."""
+
+    def __init__(self):
+        self.lib = load()
+        self.handle = ctypes.c_void_p()
+        check(self.lib.bode_ctx_create(ctypes.byref(self.handle)))
+
+    def alloc_count(self):
+        return int(self.lib.bode_ctx_alloc_count(self.handle))
+
+    def close(self):
+        if self.handle:
+            self.lib.bode_ctx_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def default_ctx_alloc_count():
+    return int(load().bode_ctx_alloc_count(None))
+
+
+def argmax_combine(records):
+    """np.argmax-style winner among packed 16-byte (float64 value, int64 index) records (host bytes / int64 array)."""
+    lib = load()
+    buf = np.ascontiguousarray(records).view(np.uint8).reshape(-1)
+    assert buf.size % 16 == 0
+    best = ctypes.c_double(0.0)
+    idx = ctypes.c_int64(-1)
+    check(lib.bode_argmax_combine(_np_ptr(buf), buf.size // 16, ctypes.byref(best), ctypes.byref(idx)))
+    return best.value, idx.value
+
+
 def ekld_score_host(X, Y, hyp, X_design, nugget_var, jitter=1e-8, form=BODE_FORM_REFERENCE, want_var=True,
-                    want_kld=False, raise_not_pd=True):
+                    want_kld=False, raise_not_pd=True, ctx=None):
     """Host-buffer call (``bode_ekld_score_host``): NumPy in, NumPy out; copies both ways inside the call."""
     lib = load()
     X = _f64(X); n, d = X.shape
@@ -140,9 +211,9 @@ def ekld_score_host(X, Y, hyp, X_design, nugget_var, jitter=1e-8, form=BODE_FORM
     best = np.zeros(1, dtype=np.int64)
     ms = np.empty(2)
     info = np.zeros(S, dtype=np.int32)
-    st = lib.bode_ekld_score_host(_np_ptr(X), _np_ptr(Y), _np_ptr(hyp), n, d, S, ndim, float(nugget_var), float(jitter),
-                                  _np_ptr(Xd), Nd, int(form), _np_ptr(score), _np_ptr(var), _np_ptr(kld), _np_ptr(best),
-                                  _np_ptr(ms), _np_ptr(info))
+    st = lib.bode_ekld_score_host_ctx(ctx.handle if ctx is not None else None, _np_ptr(X), _np_ptr(Y), _np_ptr(hyp), n, d, S,
+                                      ndim, float(nugget_var), float(jitter), _np_ptr(Xd), Nd, int(form), _np_ptr(score),
+                                      _np_ptr(var), _np_ptr(kld), _np_ptr(best), _np_ptr(ms), _np_ptr(info))
     if st != 0 and not (st == -5 and not raise_not_pd):
         check(st)
     return dict(score=score, var=var, kld=kld, argmax=int(best[0]), mu_Q=float(ms[0]), sigma_Q=float(ms[1]), info=info)

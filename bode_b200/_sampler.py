@@ -141,6 +141,18 @@ class KLSampler(object):
             from .engine import EkldEngine
             engine = EkldEngine()
         self.engine = engine
+        # Multi-GPU (one process per GPU): candidate blocks are sharded over ``process_group`` -- only when it is passed
+        # explicitly.  Everything random on the host (MCMC hyper-samples, LHS designs, a noisy objective) is drawn on the
+        # group's rank 0 and broadcast, so the ranks always score the same design under the same model.
+        self._sharded = False
+        self._lead = True
+        if process_group is not None:
+            import torch.distributed as tdist
+            if tdist.is_available() and tdist.is_initialized() and tdist.get_world_size(process_group) > 1:
+                self._sharded = True
+                self._lead = tdist.get_rank(process_group) == 0
+                if hasattr(engine, "init_nccl") and getattr(engine, "_comm", None) is None and tdist.get_backend(process_group) == "nccl":
+                    engine.init_nccl(process_group)
         self.model = self.make_model(self.X, self.Y, it=0, mcmc=self.mcmc_model)
         self.model_d = self.make_model(self.X_u, self.Y_u, it=0, mcmc=self.mcmc_model)
         self.all_p = {}
@@ -187,16 +199,12 @@ class KLSampler(object):
                 return -np.inf
             return self.get_likelihood(param, model, X, Y) + self.get_log_prior(param)
         out = np.full(param.shape[0], -np.inf)
-        ok = ~np.any(param <= 0, axis=1)
+        ok = ~np.any(param < 0, axis=1)  # same support test as the scalar path (`_sampler.py:236`)
         if np.any(ok):
             good = param[ok]
             ll = self._loglik_batch(good, X, Y)
-            d = self.X.shape[1]
-            pr = np.asarray(self.variance_prior(good[:, 0]), dtype=np.float64) * np.ones(good.shape[0])
-            for j in range(d):
-                pr = pr + self.lengthscale_prior(good[:, j + 1])
-            if self.noisy:
-                pr = pr + self.noise_prior(good[:, -1])
+            # the prior protocol is scalar (reference `_core.py:17-83`; user priors too): one call per entry
+            pr = np.array([self.get_log_prior(row) for row in good], dtype=np.float64)
             out[ok] = ll + pr
         out[np.isnan(out)] = -np.inf
         return out
@@ -205,6 +213,22 @@ class KLSampler(object):
         """Hyper-samples of the GP posterior: ``[ndarray (S, d+1 | d+2)]`` (``_sampler.py:241-275``)."""
         if not mcmc:
             raise NotImplementedError("MLE surrogate (EGO inner loop) is superseded by dense scoring")
+        if self._sharded:
+            hs = self._make_model_local(X, Y, it, last_model)[0] if self._lead else None
+            return [self._bcast(hs)]
+        return self._make_model_local(X, Y, it, last_model)
+
+    def _bcast(self, a):
+        from . import dist as _dist
+        return _dist.broadcast_array(a, group=self.process_group, device=getattr(self.engine, "device", None))
+
+    def _lead_draw(self, fn):
+        """fn() evaluated on the group's rank 0 and broadcast (unsharded: evaluated here)."""
+        if not self._sharded:
+            return fn()
+        return self._bcast(fn() if self._lead else None)
+
+    def _make_model_local(self, X, Y, it=0, last_model=None):
         if self.hyper_samples is not None:
             return [np.ascontiguousarray(self.hyper_samples(X, Y, it), dtype=np.float64)]
         d = X.shape[1]
@@ -248,8 +272,28 @@ class KLSampler(object):
         return q, (None if w.ndim != 1 else w)
 
     def _prepare(self, model, X, Y):
-        info = self.engine.prepare(X, Y, model[0], self.nugget ** 2, quad=self._quad())
+        """Factorise every hyper-sample; a failed Cholesky is retried like GPy's ``jitchol`` does inside
+        ``make_mcmc_model`` (``_sampler.py:453``), and what still fails raises instead of poisoning the scores with NaN
+        (a NaN would win the argmax, ``np.argmax`` semantics)."""
+        info = self.engine.prepare(X, Y, model[0], self.nugget ** 2, quad=self._quad(), jitchol_retries=5)
+        bad = np.nonzero(np.asarray(info.cpu() if hasattr(info, "cpu") else info) != 0)[0]
+        if bad.size:
+            from ._ext import BodeError
+            codes = np.asarray(info.cpu() if hasattr(info, "cpu") else info)[bad]
+            raise BodeError(-5, "hyper-samples %s: %s" % (bad.tolist()[:8], "invalid hyper-parameters (info = -1)" if (codes < 0).any()
+                                                          else "not positive definite, even with jitter (info = %s)" % codes.tolist()[:8]))
+        if getattr(self.engine, "jitter_used", None) is not None:
+            print('>... Cholesky retried with added jitter for %d hyper-sample(s) (GPy jitchol semantics)'
+                  % int((self.engine.jitter_used > 1e-8).sum()))
         return info
+
+    def _prepare_plain(self, model, X, Y):
+        """``_prepare`` without the quadrature override (the comparator integrates in closed form)."""
+        mode, self.ekld_mode = self.ekld_mode, 'closed'
+        try:
+            return self._prepare(model, X, Y)
+        finally:
+            self.ekld_mode = mode
 
     def get_mu_sigma(self, model, X, Y):
         """(mean_s mu_1, mean_s sigma_1): posterior mean / variance of Q averaged over hyper-samples (``:434-444``)."""
@@ -268,7 +312,7 @@ class KLSampler(object):
         model = self.model if model is None else model
         self._prepare(model, self.X, self.Y)
         mu, sigma = self.engine.mu_sigma()
-        res = _dist.sharded_score(self.engine, X_design, form=self.ekld_form, group=self.process_group)
+        res = _dist.sharded_score(self.engine, X_design, form=self.ekld_form, group=self.process_group if self._sharded else None)
         res.update(mu=mu, sigma=sigma)
         return res
 
@@ -278,13 +322,13 @@ class KLSampler(object):
 
     def update_comp_models(self, it):
         """Uncertainty-sampling comparator (``_sampler.py:502-517``): add argmax of mean_s predictive variance."""
-        x_grid = lhs(self.X.shape[1], 1000)
-        self.engine.prepare(self.X_u, self.Y_u, self.model_d[0], self.nugget ** 2)
+        x_grid = self._lead_draw(lambda: lhs(self.X.shape[1], 1000))
+        self._prepare_plain(self.model_d, self.X_u, self.Y_u)
         r = self.engine.us_variance(x_grid)
         j = int(r["best_idx"].item())
         X_u_new = x_grid[j]
         self.X_u = np.vstack([self.X_u, np.atleast_2d(X_u_new)])
-        self.Y_u = np.vstack([self.Y_u, np.atleast_2d(self.obj_func(X_u_new))])
+        self.Y_u = np.vstack([self.Y_u, np.atleast_2d(self._lead_draw(lambda: np.atleast_2d(self.obj_func(X_u_new))))])
         self.model_d = self.make_model(X=self.X_u, Y=self.Y_u, it=it, mcmc=self.mcmc_model, last_model=self.model_d)
 
     def make_plots(self, it, kld, X_design, x_best, y_obs, model=None, ekld_model=None, comp_plots=False):
@@ -321,7 +365,7 @@ class KLSampler(object):
         for i in range(self.max_it):
             print('iteration no. ', i + 1)
             if self.X_design is None:
-                X_design = lhs(self.X.shape[1], num_designs, criterion='center')
+                X_design = self._lead_draw(lambda: lhs(self.X.shape[1], num_designs, criterion='center'))
             elif X_design.shape[0] != num_designs:
                 kld_all = np.ndarray((self.max_it, X_design.shape[0]))
                 num_designs = X_design.shape[0]
@@ -346,7 +390,7 @@ class KLSampler(object):
             if verbose > 0:
                 print('>... maximum EKLD', np.max(kld))
                 print('>... run the next experiment at design: ', x_best)
-            y_obs = self.obj_func(x_best)
+            y_obs = self._lead_draw(lambda: np.atleast_2d(self.obj_func(x_best))) if self._sharded else self.obj_func(x_best)
             if verbose > 0:
                 print('>... simulated the output at the selected design: ', y_obs)
             if plots > 0:

@@ -6,6 +6,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <dlfcn.h>
+
 #include <mutex>
 #include <vector>
 
@@ -13,6 +15,7 @@
 #include "layout.h"
 #include "prepare_args.h"
 #include "score_args.h"
+#include "tuning.h"
 
 namespace bode {
 cudaError_t launch_prepare(const PrepArgs& a, cudaStream_t st);
@@ -21,10 +24,10 @@ cudaError_t launch_mu_sigma(const void* ws, const Layout& L, double* out, cudaSt
 cudaError_t launch_loglik_gather(const void* ws, const Layout& L, double* out, cudaStream_t st);
 int plan_score(const Layout& L, int64_t Nd, int sm_count, size_t smem_optin, ScorePlan* P);
 cudaError_t launch_score(const ScoreArgs& a, const ScorePlan& P, cudaStream_t st);
-cudaError_t launch_ekld(const void* ws, const Layout& L, const double* Xd, const double* xi_ovr, double* logk,
-                        const double* wkplane, int S, int64_t Nd, int form, cudaStream_t st);
+cudaError_t launch_xi(const void* ws, const Layout& L, const double* Xd, double* xi_out, int S, int64_t Nd, cudaStream_t st);
 cudaError_t launch_reduce(const double* logk, int S, int64_t Nd, int64_t idx_offset, double* score, double* var,
-                          double* part_val, int64_t* part_idx, double* best, int64_t* best_idx, cudaStream_t st);
+                          double* part_val, int64_t* part_idx, unsigned int* done_counter, double* best, int64_t* best_idx,
+                          cudaStream_t st);
 cudaError_t launch_exp_inplace(double* v, size_t n, cudaStream_t st);
 cudaError_t measure_fp64_peak(double* dmma, double* dfma);
 cudaError_t launch_rowmean(const double* hyp, int S, int ndim, int d, const double* P, int64_t Np, const double* Xq,
@@ -32,6 +35,27 @@ cudaError_t launch_rowmean(const double* hyp, int S, int ndim, int d, const doub
 cudaError_t launch_weighted_mean(const double* rm, const double* wq, int Nq, const double* wsum_ptr, int S, double* out,
                                  cudaStream_t st);
 cudaError_t launch_sum_weights(const double* wq, int Nq, double* out, cudaStream_t st);
+
+// ---- tuning knobs: the environment is read once (and again only on bode_tuning_reload) ----------------------------
+static Tuning read_tuning() {
+  auto geti = [](const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+  };
+  Tuning t;
+  t.score_variant = geti("BODE_SCORE_VARIANT", -1);
+  t.chunk_kb = geti("BODE_CHUNK_KB", 0);
+  t.waves = geti("BODE_WAVES", 0);
+  t.stages = geti("BODE_STAGES", 0);
+  t.debug_skip = geti("BODE_DEBUG_SKIP", 0);
+  t.stagger = geti("BODE_STAGGER", 0);
+  t.xik_series = geti("BODE_XIK_SERIES", 1);
+  t.prep_split = geti("BODE_PREP_SPLIT", 0);
+  return t;
+}
+static Tuning g_tuning = read_tuning();
+const Tuning& tuning() { return g_tuning; }
+void tuning_reload() { g_tuning = read_tuning(); }
 }  // namespace bode
 
 using namespace bode;
@@ -73,13 +97,104 @@ static int get_props(DevProps* p) {
 static bool shape_ok(int n, int d, int S) { return n >= 1 && d >= 1 && S >= 1; }
 static bool shape_supported(int n, int d) { return n <= BODE_MAX_N && d <= BODE_MAX_D; }
 
-// ---- host-buffer entry points --------------------------------------------------------------------------------
-struct DevBuf {
-  void* p = nullptr;
-  ~DevBuf() { if (p) cudaFree(p); }
-  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
-  template <typename T> T* as() { return static_cast<T*>(p); }
+// ---- reusable context of the host-buffer entry points -------------------------------------------------------------
+// Holds the device buffers (grow-only), a stream and nothing else: after the first call of a given size the host entry
+// points make no cudaMalloc / cudaFree (the reference's loop calls them once per outer iteration).
+struct bode_ctx {
+  std::mutex mu;
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+  };
+  enum { kX, kY, kH, kXd, kWs, kInfo, kPlane, kScore, kVar, kBest, kScr, kMs, kLl, kNumBufs };
+  Buf b[kNumBufs];
+  std::vector<int> hinfo;
+  long long n_alloc = 0;  // cudaMalloc calls made so far (tests: stays constant across repeated calls)
+  cudaError_t need(int i, size_t bytes) {
+    if (bytes == 0) bytes = 8;
+    if (b[i].cap >= bytes) return cudaSuccess;
+    if (b[i].p) cudaFree(b[i].p);
+    b[i].p = nullptr;
+    b[i].cap = 0;
+    const size_t cap = align_up(bytes + bytes / 4, 256);
+    cudaError_t e = cudaMalloc(&b[i].p, cap);
+    if (e == cudaSuccess) { b[i].cap = cap; n_alloc++; }
+    return e;
+  }
+  template <typename T> T* as(int i) { return static_cast<T*>(b[i].p); }
 };
+
+static bode_ctx* default_ctx() {
+  static bode_ctx ctx;  // process-wide context behind the ctx-less host entry points
+  return &ctx;
+}
+
+static int ctx_bind(bode_ctx* c) {
+  int dev = 0;
+  BODE_CUDA(cudaGetDevice(&dev));
+  if (c->device < 0) {
+    c->device = dev;
+    BODE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  } else if (c->device != dev) {
+    return BODE_ERR_BAD_ARG;  // a context belongs to the device it was first used on
+  }
+  return BODE_OK;
+}
+
+// ---- NCCL through dlopen: the library stays loadable (and single-GPU callers unaffected) without NCCL present ------
+// Only the five entry points the argmax exchange needs; types follow nccl.h (ncclUniqueId is 128 opaque bytes,
+// ncclResult_t / ncclDataType_t are ints, ncclChar = 0).
+struct BodeNcclId {
+  char internal[128];
+};
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, BodeNcclId, int) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi* nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    // torch's bundled libnccl.so.2 is already mapped in a torch process: the bare SONAME resolves to it
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+      api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (api.handle) break;
+    }
+    if (!api.handle) return;
+    api.GetUniqueId = reinterpret_cast<int (*)(void*)>(dlsym(api.handle, "ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<int (*)(void**, int, BodeNcclId, int)>(dlsym(api.handle, "ncclCommInitRank"));
+    api.AllGather = reinterpret_cast<int (*)(const void*, void*, size_t, int, void*, cudaStream_t)>(dlsym(api.handle, "ncclAllGather"));
+    api.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(api.handle, "ncclCommDestroy"));
+    api.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(api.handle, "ncclGetErrorString"));
+    if (!api.GetUniqueId || !api.CommInitRank || !api.AllGather || !api.CommDestroy) api.handle = nullptr;
+  });
+  return api.handle ? &api : nullptr;
+}
+static int nccl_fail(int r, const char* where) {
+  NcclApi* api = nccl_api();
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: NCCL error %d (%s)", where, r,
+           (api && api->GetErrorString) ? api->GetErrorString(r) : "?");
+  return BODE_ERR_NCCL;
+}
+
+// np.argmax ordering of (value, index) records: NaN counts as the maximum, ties go to the lowest index
+static bool rec_better(double av, int64_t ai, double bv, int64_t bi) {
+  const bool an = av != av, bn = bv != bv;
+  if (an || bn) {
+    if (an && bn) return ai < bi;
+    return an;
+  }
+  if (av > bv) return true;
+  if (av < bv) return false;
+  return ai < bi;
+}
 
 extern "C" {
 
@@ -93,6 +208,7 @@ const char* bode_strerror(int status) {
     case BODE_ERR_WORKSPACE: return "workspace too small or misaligned";
     case BODE_ERR_CUDA: return "CUDA error";
     case BODE_ERR_NOT_PD: return "covariance matrix not positive definite";
+    case BODE_ERR_NCCL: return "NCCL unavailable or NCCL error (see bode_last_cuda_error)";
     default: return "unknown status";
   }
 }
@@ -112,7 +228,27 @@ int bode_ekld_prepare_dev(const double* X, const double* Y, const double* hyp, i
   if (!shape_supported(n, d)) return BODE_ERR_UNSUPPORTED;
   PrepArgs a;
   a.X = X; a.Y = Y; a.hyp = hyp; a.n = n; a.d = d; a.S = S; a.ndim = ndim;
-  a.nugget_var = nugget_var; a.jitter = jitter;
+  a.nugget_var = nugget_var; a.jitter = jitter; a.jitter_s = nullptr;
+  a.ws = static_cast<char*>(workspace);
+  a.L = make_layout(n, d, S);
+  a.info = info;
+  a.e_ovr = nullptr;
+  a.sigma0_ovr = nullptr;
+  a.loglik_only = 0;
+  if (workspace_bytes < a.L.total_bytes || (reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return BODE_ERR_WORKSPACE;
+  BODE_CUDA(launch_prepare(a, static_cast<cudaStream_t>(stream)));
+  return BODE_OK;
+}
+
+int bode_ekld_prepare_jitter_dev(const double* X, const double* Y, const double* hyp, int n, int d, int S, int ndim,
+                                 double nugget_var, const double* jitter_per_sample, void* workspace, size_t workspace_bytes,
+                                 int* info, void* stream) {
+  if (!X || !Y || !hyp || !workspace || !info || !jitter_per_sample || !shape_ok(n, d, S)) return BODE_ERR_BAD_ARG;
+  if (ndim != d + 1 && ndim != d + 2) return BODE_ERR_BAD_ARG;
+  if (!shape_supported(n, d)) return BODE_ERR_UNSUPPORTED;
+  PrepArgs a;
+  a.X = X; a.Y = Y; a.hyp = hyp; a.n = n; a.d = d; a.S = S; a.ndim = ndim;
+  a.nugget_var = nugget_var; a.jitter = 0.0; a.jitter_s = jitter_per_sample;
   a.ws = static_cast<char*>(workspace);
   a.L = make_layout(n, d, S);
   a.info = info;
@@ -163,7 +299,7 @@ int bode_ekld_prepare_quad_dev(const double* X, const double* Y, const double* h
   BODE_CUDA(launch_weighted_mean(rmq, wq, Nq, wsp, S, s0, st));                  // sigma0_q
   PrepArgs a;
   a.X = X; a.Y = Y; a.hyp = hyp; a.n = n; a.d = d; a.S = S; a.ndim = ndim;
-  a.nugget_var = nugget_var; a.jitter = jitter;
+  a.nugget_var = nugget_var; a.jitter = jitter; a.jitter_s = nullptr;
   a.ws = static_cast<char*>(workspace);
   a.L = make_layout(n, d, S);
   a.info = info;
@@ -183,7 +319,7 @@ int bode_gp_loglik_dev(const double* X, const double* Y, const double* hyp, int 
   if (!shape_supported(n, d)) return BODE_ERR_UNSUPPORTED;
   PrepArgs a;
   a.X = X; a.Y = Y; a.hyp = hyp; a.n = n; a.d = d; a.S = S; a.ndim = ndim;
-  a.nugget_var = nugget_var; a.jitter = jitter;
+  a.nugget_var = nugget_var; a.jitter = jitter; a.jitter_s = nullptr;
   a.ws = static_cast<char*>(workspace);
   a.L = make_layout(n, d, S);
   a.info = info;
@@ -211,21 +347,22 @@ int bode_ekld_mu_sigma_dev(const void* workspace, int n, int d, int S, double* o
   return BODE_OK;
 }
 
+// scratch = [done counter + packed (best, idx) record: 256 B] [block argmax values] [block argmax indices] [S*Nd plane, if S > 0]
 static size_t score_partials_bytes(int64_t Nd) {
   const size_t nb = (size_t)((Nd + 255) / 256);
-  return align_up(nb * sizeof(double), 256) + align_up(nb * sizeof(int64_t), 256);
+  return 256 + align_up(nb * sizeof(double), 256) + align_up(nb * sizeof(int64_t), 256);
 }
 
 size_t bode_ekld_score_scratch_bytes(int64_t Nd, int S) {
-  if (Nd < 1 || S < 1) return 0;
-  return score_partials_bytes(Nd) + align_up(sizeof(double) * (size_t)S * (size_t)Nd, 256);  // argmax partials + v plane
+  if (Nd < 1 || S < 0) return 0;
+  return score_partials_bytes(Nd) + align_up(sizeof(double) * (size_t)S * (size_t)Nd, 256);
 }
 
 static int score_common(const void* workspace, int n, int d, int S, const double* Xd, int64_t Nd, int64_t idx_offset,
                         int form, int mode, const double* xi_ovr, double* logk, double* score, double* var, double* best,
                         int64_t* best_idx, void* scratch, void* stream, float* kernel_ms, void* ev_start = nullptr,
                         void* ev_stop = nullptr) {
-  if (!workspace || !Xd || !logk || !score || !best || !best_idx || !scratch || !shape_ok(n, d, S) || Nd < 1)
+  if (!workspace || !Xd || !score || !best || !best_idx || !scratch || !shape_ok(n, d, S) || Nd < 1)
     return BODE_ERR_BAD_ARG;
   if (form != BODE_FORM_REFERENCE && form != BODE_FORM_LOG1P) return BODE_ERR_BAD_ARG;
   if (!shape_supported(n, d)) return BODE_ERR_UNSUPPORTED;
@@ -235,20 +372,26 @@ static int score_common(const void* workspace, int n, int d, int S, const double
   ScorePlan P;
   const Layout L = make_layout(n, d, S);
   if (plan_score(L, Nd, props.sm_count, props.smem_optin, &P) != 0) return BODE_ERR_UNSUPPORTED;
+  char* scr = static_cast<char*>(scratch);
+  const size_t nb = (size_t)((Nd + 255) / 256);
+  unsigned int* done_counter = reinterpret_cast<unsigned int*>(scr);
+  double* part_val = reinterpret_cast<double*>(scr + 256);
+  int64_t* part_idx = reinterpret_cast<int64_t*>(scr + 256 + align_up(nb * sizeof(double), 256));
+  // the S x Nd plane: xik(x) in, log EKLD (or sigma_x) out; the caller's logk buffer if given, else the tail of scratch
+  double* plane = logk ? logk : reinterpret_cast<double*>(scr + score_partials_bytes(Nd));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   ScoreArgs a;
-  a.ws = workspace; a.L = L; a.Xd = Xd; a.Nd = Nd; a.logk = logk; a.S = S;
-  a.vplane = reinterpret_cast<double*>(static_cast<char*>(scratch) + score_partials_bytes(Nd));
+  a.ws = workspace; a.L = L; a.Xd = Xd; a.Nd = Nd; a.S = S;
+  a.xi = xi_ovr ? xi_ovr : plane;
+  a.done_counter = done_counter;
+  a.out = plane;
   a.sc = P.sc; a.ntiles = P.ntiles; a.form = form; a.mode = mode;
-  {
-    const char* dbg = getenv("BODE_DEBUG_SKIP");
-    a.debug_skip = dbg ? atoi(dbg) : 0;
-    const char* sg = getenv("BODE_STAGGER");
-    a.stagger = sg ? atoi(sg) : 0;
-  }
+  a.debug_skip = tuning().debug_skip;
+  a.stagger = tuning().stagger;
   a.stages = P.stages; a.chunk_max = P.chunk_max; a.nchunks = P.nchunks; a.u_global = P.u_global;
   memcpy(a.chunk_g0, P.chunk_g0, sizeof(a.chunk_g0));
   memcpy(a.tile_id, P.tile_id, sizeof(a.tile_id));
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (mode == kModeEkld && !xi_ovr) BODE_CUDA(launch_xi(workspace, L, Xd, plane, S, Nd, st));
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (kernel_ms) {
     BODE_CUDA(cudaEventCreate(&ev0));
@@ -259,11 +402,7 @@ static int score_common(const void* workspace, int n, int d, int S, const double
   BODE_CUDA(launch_score(a, P, st));
   if (ev_stop) BODE_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_stop), st));
   if (kernel_ms) BODE_CUDA(cudaEventRecord(ev1, st));
-  if (mode == kModeEkld) BODE_CUDA(launch_ekld(workspace, L, Xd, xi_ovr, logk, a.vplane, S, Nd, form, st));
-  const size_t nb = (size_t)((Nd + 255) / 256);
-  double* part_val = static_cast<double*>(scratch);
-  int64_t* part_idx = reinterpret_cast<int64_t*>(static_cast<char*>(scratch) + align_up(nb * sizeof(double), 256));
-  BODE_CUDA(launch_reduce(logk, S, Nd, idx_offset, score, var, part_val, part_idx, best, best_idx, st));
+  BODE_CUDA(launch_reduce(plane, S, Nd, idx_offset, score, var, part_val, part_idx, done_counter, best, best_idx, st));
   if (kernel_ms) {
     BODE_CUDA(cudaEventSynchronize(ev1));
     BODE_CUDA(cudaEventElapsedTime(kernel_ms, ev0, ev1));
@@ -314,80 +453,183 @@ int bode_us_variance_dev(const void* workspace, int n, int d, int S, const doubl
                       nullptr, best, best_idx, scratch, stream, nullptr);
 }
 
-int bode_ekld_score_host(const double* X, const double* Y, const double* hyp, int n, int d, int S, int ndim,
-                         double nugget_var, double jitter, const double* X_design, int64_t Nd, int form,
-                         double* score, double* var, double* kld, int64_t* best_idx, double* mu_sigma, int* info) {
+int bode_ctx_create(bode_ctx** out) {
+  if (!out) return BODE_ERR_BAD_ARG;
+  *out = new (std::nothrow) bode_ctx();
+  return *out ? BODE_OK : BODE_ERR_BAD_ARG;
+}
+
+int bode_ctx_destroy(bode_ctx* c) {
+  if (!c || c == default_ctx()) return BODE_ERR_BAD_ARG;
+  for (auto& buf : c->b)
+    if (buf.p) cudaFree(buf.p);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return BODE_OK;
+}
+
+long long bode_ctx_alloc_count(bode_ctx* c) {
+  if (!c) c = default_ctx();
+  std::lock_guard<std::mutex> lk(c->mu);
+  return c->n_alloc;
+}
+
+int bode_ekld_score_host_ctx(bode_ctx* c, const double* X, const double* Y, const double* hyp, int n, int d, int S, int ndim,
+                             double nugget_var, double jitter, const double* X_design, int64_t Nd, int form,
+                             double* score, double* var, double* kld, int64_t* best_idx, double* mu_sigma, int* info) {
   if (!X || !Y || !hyp || !X_design || !score || !shape_ok(n, d, S) || Nd < 1) return BODE_ERR_BAD_ARG;
   if (ndim != d + 1 && ndim != d + 2) return BODE_ERR_BAD_ARG;
   if (!shape_supported(n, d)) return BODE_ERR_UNSUPPORTED;
-  const size_t wsb = bode_ekld_workspace_bytes(n, d, S);
-  DevBuf dX, dY, dH, dXd, dWs, dInfo, dLogk, dScore, dVar, dBest, dBestIdx, dScr, dMs;
-  BODE_CUDA(dX.alloc(sizeof(double) * n * d));
-  BODE_CUDA(dY.alloc(sizeof(double) * n));
-  BODE_CUDA(dH.alloc(sizeof(double) * S * ndim));
-  BODE_CUDA(dXd.alloc(sizeof(double) * Nd * d));
-  BODE_CUDA(dWs.alloc(wsb));
-  BODE_CUDA(dInfo.alloc(sizeof(int) * S));
-  BODE_CUDA(dLogk.alloc(sizeof(double) * (size_t)S * Nd));
-  BODE_CUDA(dScore.alloc(sizeof(double) * Nd));
-  BODE_CUDA(dVar.alloc(sizeof(double) * Nd));
-  BODE_CUDA(dBest.alloc(sizeof(double)));
-  BODE_CUDA(dBestIdx.alloc(sizeof(int64_t)));
-  BODE_CUDA(dScr.alloc(bode_ekld_score_scratch_bytes(Nd, S)));
-  BODE_CUDA(dMs.alloc(2 * sizeof(double)));
-  BODE_CUDA(cudaMemcpy(dX.p, X, sizeof(double) * n * d, cudaMemcpyHostToDevice));
-  BODE_CUDA(cudaMemcpy(dY.p, Y, sizeof(double) * n, cudaMemcpyHostToDevice));
-  BODE_CUDA(cudaMemcpy(dH.p, hyp, sizeof(double) * S * ndim, cudaMemcpyHostToDevice));
-  BODE_CUDA(cudaMemcpy(dXd.p, X_design, sizeof(double) * Nd * d, cudaMemcpyHostToDevice));
-  int rc = bode_ekld_prepare_dev(dX.as<double>(), dY.as<double>(), dH.as<double>(), n, d, S, ndim, nugget_var, jitter,
-                                 dWs.p, wsb, dInfo.as<int>(), nullptr);
+  if (!c) c = default_ctx();
+  std::lock_guard<std::mutex> lk(c->mu);
+  int rc = ctx_bind(c);
   if (rc != BODE_OK) return rc;
-  rc = bode_ekld_score_dev(dWs.p, n, d, S, dXd.as<double>(), Nd, 0, form, dLogk.as<double>(), dScore.as<double>(),
-                           var ? dVar.as<double>() : nullptr, dBest.as<double>(), dBestIdx.as<int64_t>(), dScr.p, nullptr);
+  typedef bode_ctx B;
+  const size_t wsb = bode_ekld_workspace_bytes(n, d, S);
+  BODE_CUDA(c->need(B::kX, sizeof(double) * n * d));
+  BODE_CUDA(c->need(B::kY, sizeof(double) * n));
+  BODE_CUDA(c->need(B::kH, sizeof(double) * S * ndim));
+  BODE_CUDA(c->need(B::kXd, sizeof(double) * Nd * d));
+  BODE_CUDA(c->need(B::kWs, wsb));
+  BODE_CUDA(c->need(B::kInfo, sizeof(int) * S));
+  BODE_CUDA(c->need(B::kPlane, sizeof(double) * (size_t)S * Nd));
+  BODE_CUDA(c->need(B::kScore, sizeof(double) * Nd));
+  BODE_CUDA(c->need(B::kVar, sizeof(double) * Nd));
+  BODE_CUDA(c->need(B::kBest, 64));
+  BODE_CUDA(c->need(B::kScr, bode_ekld_score_scratch_bytes(Nd, 0)));
+  BODE_CUDA(c->need(B::kMs, 2 * sizeof(double)));
+  cudaStream_t st = c->stream;
+  BODE_CUDA(cudaMemcpyAsync(c->b[B::kX].p, X, sizeof(double) * n * d, cudaMemcpyHostToDevice, st));
+  BODE_CUDA(cudaMemcpyAsync(c->b[B::kY].p, Y, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  BODE_CUDA(cudaMemcpyAsync(c->b[B::kH].p, hyp, sizeof(double) * S * ndim, cudaMemcpyHostToDevice, st));
+  BODE_CUDA(cudaMemcpyAsync(c->b[B::kXd].p, X_design, sizeof(double) * Nd * d, cudaMemcpyHostToDevice, st));
+  rc = bode_ekld_prepare_dev(c->as<double>(B::kX), c->as<double>(B::kY), c->as<double>(B::kH), n, d, S, ndim, nugget_var, jitter,
+                             c->b[B::kWs].p, wsb, c->as<int>(B::kInfo), st);
+  if (rc != BODE_OK) return rc;
+  double* dbest = c->as<double>(B::kBest);
+  int64_t* dbest_idx = reinterpret_cast<int64_t*>(dbest + 1);
+  rc = bode_ekld_score_dev(c->b[B::kWs].p, n, d, S, c->as<double>(B::kXd), Nd, 0, form, c->as<double>(B::kPlane),
+                           c->as<double>(B::kScore), var ? c->as<double>(B::kVar) : nullptr, dbest, dbest_idx, c->b[B::kScr].p, st);
   if (rc != BODE_OK) return rc;
   if (mu_sigma) {
-    rc = bode_ekld_mu_sigma_dev(dWs.p, n, d, S, dMs.as<double>(), nullptr);
+    rc = bode_ekld_mu_sigma_dev(c->b[B::kWs].p, n, d, S, c->as<double>(B::kMs), st);
     if (rc != BODE_OK) return rc;
-    BODE_CUDA(cudaMemcpy(mu_sigma, dMs.p, 2 * sizeof(double), cudaMemcpyDeviceToHost));
+    BODE_CUDA(cudaMemcpyAsync(mu_sigma, c->b[B::kMs].p, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
   }
-  BODE_CUDA(cudaMemcpy(score, dScore.p, sizeof(double) * Nd, cudaMemcpyDeviceToHost));
-  if (var) BODE_CUDA(cudaMemcpy(var, dVar.p, sizeof(double) * Nd, cudaMemcpyDeviceToHost));
-  if (best_idx) BODE_CUDA(cudaMemcpy(best_idx, dBestIdx.p, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  BODE_CUDA(cudaMemcpyAsync(score, c->b[B::kScore].p, sizeof(double) * Nd, cudaMemcpyDeviceToHost, st));
+  if (var) BODE_CUDA(cudaMemcpyAsync(var, c->b[B::kVar].p, sizeof(double) * Nd, cudaMemcpyDeviceToHost, st));
+  if (best_idx) BODE_CUDA(cudaMemcpyAsync(best_idx, dbest_idx, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   if (kld) {
-    BODE_CUDA(launch_exp_inplace(dLogk.as<double>(), (size_t)S * Nd, nullptr));
-    BODE_CUDA(cudaMemcpy(kld, dLogk.p, sizeof(double) * (size_t)S * Nd, cudaMemcpyDeviceToHost));
+    BODE_CUDA(launch_exp_inplace(c->as<double>(B::kPlane), (size_t)S * Nd, st));
+    BODE_CUDA(cudaMemcpyAsync(kld, c->b[B::kPlane].p, sizeof(double) * (size_t)S * Nd, cudaMemcpyDeviceToHost, st));
   }
-  std::vector<int> hinfo(S);
-  BODE_CUDA(cudaMemcpy(hinfo.data(), dInfo.p, sizeof(int) * S, cudaMemcpyDeviceToHost));
-  BODE_CUDA(cudaDeviceSynchronize());
+  c->hinfo.resize(S);
+  BODE_CUDA(cudaMemcpyAsync(c->hinfo.data(), c->b[B::kInfo].p, sizeof(int) * S, cudaMemcpyDeviceToHost, st));
+  BODE_CUDA(cudaStreamSynchronize(st));
   int bad = 0;
   for (int s = 0; s < S; s++) {
-    if (info) info[s] = hinfo[s];
-    if (hinfo[s] != 0) bad = 1;
+    if (info) info[s] = c->hinfo[s];
+    if (c->hinfo[s] != 0) bad = 1;
   }
   return bad ? BODE_ERR_NOT_PD : BODE_OK;
 }
 
-int bode_gp_loglik_host(const double* X, const double* Y, const double* hyp, int n, int d, int S, int ndim,
-                        double nugget_var, double jitter, double* loglik) {
+int bode_ekld_score_host(const double* X, const double* Y, const double* hyp, int n, int d, int S, int ndim,
+                         double nugget_var, double jitter, const double* X_design, int64_t Nd, int form,
+                         double* score, double* var, double* kld, int64_t* best_idx, double* mu_sigma, int* info) {
+  return bode_ekld_score_host_ctx(nullptr, X, Y, hyp, n, d, S, ndim, nugget_var, jitter, X_design, Nd, form, score, var, kld,
+                                  best_idx, mu_sigma, info);
+}
+
+int bode_gp_loglik_host_ctx(bode_ctx* c, const double* X, const double* Y, const double* hyp, int n, int d, int S, int ndim,
+                            double nugget_var, double jitter, double* loglik) {
   if (!X || !Y || !hyp || !loglik || !shape_ok(n, d, S)) return BODE_ERR_BAD_ARG;
   if (ndim != d + 1 && ndim != d + 2) return BODE_ERR_BAD_ARG;
   if (!shape_supported(n, d)) return BODE_ERR_UNSUPPORTED;
-  const size_t wsb = bode_ekld_workspace_bytes(n, d, S);
-  DevBuf dX, dY, dH, dWs, dInfo, dT;
-  BODE_CUDA(dX.alloc(sizeof(double) * n * d));
-  BODE_CUDA(dY.alloc(sizeof(double) * n));
-  BODE_CUDA(dH.alloc(sizeof(double) * S * ndim));
-  BODE_CUDA(dWs.alloc(wsb));
-  BODE_CUDA(dInfo.alloc(sizeof(int) * S));
-  BODE_CUDA(dT.alloc(sizeof(double) * S * kConsts));
-  BODE_CUDA(cudaMemcpy(dX.p, X, sizeof(double) * n * d, cudaMemcpyHostToDevice));
-  BODE_CUDA(cudaMemcpy(dY.p, Y, sizeof(double) * n, cudaMemcpyHostToDevice));
-  BODE_CUDA(cudaMemcpy(dH.p, hyp, sizeof(double) * S * ndim, cudaMemcpyHostToDevice));
-  int rc = bode_gp_loglik_dev(dX.as<double>(), dY.as<double>(), dH.as<double>(), n, d, S, ndim, nugget_var, jitter, dWs.p, wsb,
-                              dInfo.as<int>(), dT.as<double>(), nullptr);
+  if (!c) c = default_ctx();
+  std::lock_guard<std::mutex> lk(c->mu);
+  int rc = ctx_bind(c);
   if (rc != BODE_OK) return rc;
-  BODE_CUDA(cudaMemcpy(loglik, dT.p, sizeof(double) * S, cudaMemcpyDeviceToHost));
+  typedef bode_ctx B;
+  const size_t wsb = bode_ekld_workspace_bytes(n, d, S);
+  BODE_CUDA(c->need(B::kX, sizeof(double) * n * d));
+  BODE_CUDA(c->need(B::kY, sizeof(double) * n));
+  BODE_CUDA(c->need(B::kH, sizeof(double) * S * ndim));
+  BODE_CUDA(c->need(B::kWs, wsb));
+  BODE_CUDA(c->need(B::kInfo, sizeof(int) * S));
+  BODE_CUDA(c->need(B::kLl, sizeof(double) * S));
+  cudaStream_t st = c->stream;
+  BODE_CUDA(cudaMemcpyAsync(c->b[B::kX].p, X, sizeof(double) * n * d, cudaMemcpyHostToDevice, st));
+  BODE_CUDA(cudaMemcpyAsync(c->b[B::kY].p, Y, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  BODE_CUDA(cudaMemcpyAsync(c->b[B::kH].p, hyp, sizeof(double) * S * ndim, cudaMemcpyHostToDevice, st));
+  rc = bode_gp_loglik_dev(c->as<double>(B::kX), c->as<double>(B::kY), c->as<double>(B::kH), n, d, S, ndim, nugget_var, jitter,
+                          c->b[B::kWs].p, wsb, c->as<int>(B::kInfo), c->as<double>(B::kLl), st);
+  if (rc != BODE_OK) return rc;
+  BODE_CUDA(cudaMemcpyAsync(loglik, c->b[B::kLl].p, sizeof(double) * S, cudaMemcpyDeviceToHost, st));
+  BODE_CUDA(cudaStreamSynchronize(st));
+  return BODE_OK;
+}
+
+int bode_gp_loglik_host(const double* X, const double* Y, const double* hyp, int n, int d, int S, int ndim,
+                        double nugget_var, double jitter, double* loglik) {
+  return bode_gp_loglik_host_ctx(nullptr, X, Y, hyp, n, d, S, ndim, nugget_var, jitter, loglik);
+}
+
+int bode_tuning_reload(void) {
+  tuning_reload();
+  return BODE_OK;
+}
+
+// ---- multi-GPU argmax exchange: one 16-byte all-gather on the compute stream --------------------------
+int bode_nccl_unique_id(void* id128) {
+  if (!id128) return BODE_ERR_BAD_ARG;
+  NcclApi* api = nccl_api();
+  if (!api) return BODE_ERR_NCCL;
+  const int r = api->GetUniqueId(id128);
+  return r == 0 ? BODE_OK : nccl_fail(r, "ncclGetUniqueId");
+}
+
+int bode_nccl_comm_create(const void* id128, int world, int rank, void** comm) {
+  if (!id128 || !comm || world < 1 || rank < 0 || rank >= world) return BODE_ERR_BAD_ARG;
+  NcclApi* api = nccl_api();
+  if (!api) return BODE_ERR_NCCL;
+  BodeNcclId id;
+  memcpy(&id, id128, sizeof(id));
+  const int r = api->CommInitRank(comm, world, id, rank);
+  return r == 0 ? BODE_OK : nccl_fail(r, "ncclCommInitRank");
+}
+
+int bode_nccl_comm_destroy(void* comm) {
+  if (!comm) return BODE_ERR_BAD_ARG;
+  NcclApi* api = nccl_api();
+  if (!api) return BODE_ERR_NCCL;
+  const int r = api->CommDestroy(comm);
+  return r == 0 ? BODE_OK : nccl_fail(r, "ncclCommDestroy");
+}
+
+int bode_ekld_argmax_nccl(void* comm, const void* best_rec, void* gathered, void* stream) {
+  if (!comm || !best_rec || !gathered) return BODE_ERR_BAD_ARG;
+  NcclApi* api = nccl_api();
+  if (!api) return BODE_ERR_NCCL;
+  const int r = api->AllGather(best_rec, gathered, 16, /*ncclChar*/ 0, comm, static_cast<cudaStream_t>(stream));
+  return r == 0 ? BODE_OK : nccl_fail(r, "ncclAllGather");
+}
+
+int bode_argmax_combine(const void* records, int count, double* best, int64_t* best_idx) {
+  if (!records || count < 1 || !best || !best_idx) return BODE_ERR_BAD_ARG;
+  const char* p = static_cast<const char*>(records);
+  double bv = 0.0;
+  int64_t bi = -1;
+  for (int i = 0; i < count; i++) {
+    double v;
+    int64_t idx;
+    memcpy(&v, p + 16 * i, 8);
+    memcpy(&idx, p + 16 * i + 8, 8);
+    if (idx < 0) continue;  // a rank without candidates
+    if (bi < 0 || rec_better(v, idx, bv, bi)) { bv = v; bi = idx; }
+  }
+  *best = bv;
+  *best_idx = bi;
   return BODE_OK;
 }
 

@@ -95,8 +95,60 @@ cudaError_t debug_copy_prepare_timeline(long long* host) { return cudaMemcpyFrom
 #define TP(i) do { } while (0)
 #endif
 
+// ---- even Chebyshev series of the xik factors (candidate-independent part of xik(x), reference _core.py:86-92) -----
+// F_k(x) = sqrt(pi)/sqrt(2) * ell_k * (erf((1-x) c_k) - erf((0-x) c_k)) is symmetric about x = 1/2, so with u = 2x-1 it is
+// a series in T_2j(u) = T_j(w), w = 2u^2 - 1.  One CTA per (sample, dimension): sample F at the 64 Gauss-Chebyshev nodes
+// w_i = cos(theta_i) (u_i = cos(theta_i / 2) exactly), a_j = (2/64) sum_i F_i cos(j theta_i) with the cosines taken
+// through cospi of an exactly reduced argument, cut the series where the coefficients drop under the rounding floor of
+// this very sum (4e-16 a_0).  The EKLD kernel then spends 2 n + 6 operations per factor instead of two erf (~130).
+// Runs inside the k_prepare launch on the blocks with blockIdx.x >= S (they land on the SMs the S factorisation CTAs leave
+// idle): block S + s * ceil(d/4) + q handles dimensions 4q..4q+3 of sample s, 64 threads per dimension.
+__device__ __forceinline__ void xik_coef_block(const double* __restrict__ hyp, int ndim, int d, char* ws, const Layout& L, int s, int k0,
+                                               double* F /*[4][64]*/, double* A /*[4][64]*/) {
+  const int kq = threadIdx.x >> 6, i = threadIdx.x & 63, k = k0 + kq;
+  const bool on = k < d;
+  if (on) {
+    const double ell = hyp[(size_t)s * ndim + 1 + k];
+    const double c = 1.0 / (1.4142135623730951 * ell);
+    const double u = cospi(((double)i + 0.5) / (2.0 * kXcNodes));  // cos(theta_i / 2), theta_i = pi (i + 1/2) / 64
+    const double x = 0.5 * (u + 1.0);
+    F[kq * kXcNodes + i] = 1.2533141373155001 * ell * (erf((1.0 - x) * c) - erf((0.0 - x) * c));
+  }
+  __syncthreads();
+  if (on) {
+    double acc = 0.0;
+    for (int m = 0; m < kXcNodes; m++) {
+      const int r = (i * (2 * m + 1)) & (4 * kXcNodes - 1);  // j theta_m = pi r / 128 (mod 2 pi), j = this thread
+      acc = fma(F[kq * kXcNodes + m], cospi((double)r / (2.0 * kXcNodes)), acc);
+    }
+    A[kq * kXcNodes + i] = acc * (2.0 / kXcNodes);
+  }
+  __syncthreads();
+  if (!on) return;
+  const double* Ak = A + kq * kXcNodes;
+  double* out = reinterpret_cast<double*>(ws + L.off_xc) + (size_t)s * L.xc_doubles + (size_t)k * kXcStride;
+  if (i == 0) {
+    const double floor_ = 4e-16 * fabs(Ak[0]);
+    int n = 0;
+    bool ok = Ak[0] == Ak[0];
+    for (int j = 0; j < kXcNodes; j++) {
+      if (!(fabs(Ak[j]) <= floor_)) {       // (also true for NaN)
+        if (j < kXcMax) n = j + 1;
+        else ok = false;                    // not converged within kXcMax terms: erf path
+      }
+    }
+    out[0] = ok ? (double)n : 0.0;
+  }
+  if (i < kXcMax) out[1 + i] = (i == 0) ? 0.5 * Ak[0] : Ak[i];
+}
+
 __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
   extern __shared__ __align__(16) double sm[];
+  if ((int)blockIdx.x >= a.S) {  // Chebyshev series of the xik factors (blocks beyond the S factorisation CTAs)
+    const int per = (a.d + 3) / 4, b = (int)blockIdx.x - a.S;
+    xik_coef_block(a.hyp, a.ndim, a.d, a.ws, a.L, b / per, 4 * (b % per), sm, sm + 4 * kXcNodes);
+    return;
+  }
   const int s = blockIdx.x, tid = threadIdx.x;
   const int n = a.n, d = a.d, npad = a.L.npad;
   TP(0);
@@ -183,6 +235,7 @@ __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
   // ---- A = K + (noise + jitter) I, lower triangle, rows 0..n-1 ------------------------------------------------
   // strictly-lower entries, flat triangular index so that all threads carry the same number of exp() calls
   // (the observations are staged in the panel buffer, free until the factorisation starts, when they fit)
+  const double jit = a.jitter_s ? a.jitter_s[s] : a.jitter;
   const bool x_smem = d <= kNB;
   if (x_smem) {
     for (int idx = tid; idx < n * d; idx += kPrepThreads) Ljp[idx] = a.X[idx];
@@ -206,7 +259,7 @@ __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
   }
   for (int idx = tid; idx < n * npad; idx += kPrepThreads) {
     const int i = idx / npad, j = idx - i * npad;
-    if (j == i) Lw[idx] = ss + (noise + a.jitter);  // GPy: diag.add(Ky, variance + 1e-8)
+    if (j == i) Lw[idx] = ss + (noise + jit);  // GPy: diag.add(Ky, variance + 1e-8)
     else if (j > i) Lw[idx] = 0.0;
   }
   __syncthreads();
@@ -412,56 +465,28 @@ __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
 }
 
 
-// ---- even Chebyshev series of the xik factors (candidate-independent part of xik(x), reference _core.py:86-92) -----
-// F_k(x) = sqrt(pi)/sqrt(2) * ell_k * (erf((1-x) c_k) - erf((0-x) c_k)) is symmetric about x = 1/2, so with u = 2x-1 it is
-// a series in T_2j(u) = T_j(w), w = 2u^2 - 1.  One CTA per (sample, dimension): sample F at the 64 Gauss-Chebyshev nodes
-// w_i = cos(theta_i) (u_i = cos(theta_i / 2) exactly), a_j = (2/64) sum_i F_i cos(j theta_i) with the cosines taken
-// through cospi of an exactly reduced argument, cut the series where the coefficients drop under the rounding floor of
-// this very sum (4e-16 a_0).  The EKLD kernel then spends 2 n + 6 operations per factor instead of two erf (~130).
-__global__ void __launch_bounds__(kXcNodes) k_xik_coef(const double* __restrict__ hyp, int ndim, int d, char* ws, Layout L) {
-  __shared__ double F[kXcNodes], A[kXcNodes];
-  const int s = blockIdx.x, k = blockIdx.y, i = threadIdx.x;
-  const double ell = hyp[(size_t)s * ndim + 1 + k];
-  const double c = 1.0 / (1.4142135623730951 * ell);
-  const double u = cospi(((double)i + 0.5) / (2.0 * kXcNodes));  // cos(theta_i / 2), theta_i = pi (i + 1/2) / 64
-  const double x = 0.5 * (u + 1.0);
-  F[i] = 1.2533141373155001 * ell * (erf((1.0 - x) * c) - erf((0.0 - x) * c));
-  __syncthreads();
-  double acc = 0.0;
-  for (int m = 0; m < kXcNodes; m++) {
-    const int r = (i * (2 * m + 1)) & (4 * kXcNodes - 1);  // j theta_m = pi r / 128 (mod 2 pi), j = this thread
-    acc = fma(F[m], cospi((double)r / (2.0 * kXcNodes)), acc);
-  }
-  A[i] = acc * (2.0 / kXcNodes);
-  __syncthreads();
-  double* out = reinterpret_cast<double*>(ws + L.off_xc) + (size_t)s * L.xc_doubles + (size_t)k * kXcStride;
-  if (i == 0) {
-    const double floor_ = 4e-16 * fabs(A[0]);
-    int n = 0;
-    bool ok = A[0] == A[0];
-    for (int j = 0; j < kXcNodes; j++) {
-      if (!(fabs(A[j]) <= floor_)) {       // (also true for NaN)
-        if (j < kXcMax) n = j + 1;
-        else ok = false;                    // not converged within kXcMax terms: erf path
-      }
-    }
-    out[0] = ok ? (double)n : 0.0;
-  }
-  if (i < kXcMax) out[1 + i] = (i == 0) ? 0.5 * A[0] : A[i];
-}
-
 size_t prepare_smem_bytes(const Layout& L) {
-  return sizeof(double) * ((size_t)L.npad * kNB + kNB * kNB + kNB + 8 + 2 * kCkPad + kTab64 + L.npad);
+  const size_t fact = (size_t)L.npad * kNB + kNB * kNB + kNB + 8 + 2 * kCkPad + kTab64 + L.npad;
+  const size_t coef = 8 * (size_t)kXcNodes;  // the series blocks of the same launch
+  return sizeof(double) * (fact > coef ? fact : coef);
 }
 
 cudaError_t launch_prepare(const PrepArgs& a, cudaStream_t st) {
   const size_t smem = prepare_smem_bytes(a.L);
-  cudaError_t e = cudaFuncSetAttribute(k_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static thread_local int attr_dev = -1;
+  static thread_local size_t attr_smem = 0;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  k_prepare<<<a.S, kPrepThreads, smem, st>>>(a);
-  e = cudaGetLastError();
-  if (e != cudaSuccess || a.loglik_only) return e;
-  k_xik_coef<<<dim3((unsigned)a.S, (unsigned)a.d), kXcNodes, 0, st>>>(a.hyp, a.ndim, a.d, a.ws, a.L);
+  if (dev != attr_dev || smem > attr_smem) {
+    e = cudaFuncSetAttribute(k_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_dev = dev;
+    attr_smem = smem;
+  }
+  // S factorisation CTAs, plus (scoring state only) S * ceil(d/4) small CTAs for the xik series
+  const int extra = a.loglik_only ? 0 : a.S * ((a.d + 3) / 4);
+  k_prepare<<<a.S + extra, kPrepThreads, smem, st>>>(a);
   return cudaGetLastError();
 }
 

@@ -9,6 +9,7 @@ struct PrepArgs {
   const double* hyp;  // S*ndim
   int n, d, S, ndim;
   double nugget_var, jitter;
+  const double* jitter_s;    // S (nullable): per-sample diagonal addition replacing `jitter` (GPy's jitchol retries)
   char* ws;
   Layout L;
   int* info;  // S

@@ -118,16 +118,21 @@ cudaError_t launch_rowmean(const double* hyp, int S, int ndim, int d, const doub
   const int dpad = (d + 1) & ~1;
   const size_t smem = sizeof(double) * ((size_t)kRmChunk * dpad + kRmChunk + kTabPad + kCkPad);
   const dim3 grid((unsigned)((Np + kRmThreads - 1) / kRmThreads), (unsigned)S);
-  cudaError_t e;
-  if (wq) {
-    e = cudaFuncSetAttribute(k_rowmean<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // (the largest configuration, d = 16, needs 72 KB: opt in once per device)
+  static thread_local int attr_dev = -1;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev != attr_dev) {
+    const int max_smem = (int)(sizeof(double) * ((size_t)kRmChunk * 16 + kRmChunk + kTabPad + kCkPad));
+    e = cudaFuncSetAttribute(k_rowmean<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     if (e != cudaSuccess) return e;
-    k_rowmean<true><<<grid, kRmThreads, smem, st>>>(hyp, ndim, d, P, Np, Xq, wq, Nq, wsum_ptr, out);
-  } else {
-    e = cudaFuncSetAttribute(k_rowmean<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(k_rowmean<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     if (e != cudaSuccess) return e;
-    k_rowmean<false><<<grid, kRmThreads, smem, st>>>(hyp, ndim, d, P, Np, Xq, wq, Nq, nullptr, out);
+    attr_dev = dev;
   }
+  if (wq) k_rowmean<true><<<grid, kRmThreads, smem, st>>>(hyp, ndim, d, P, Np, Xq, wq, Nq, wsum_ptr, out);
+  else k_rowmean<false><<<grid, kRmThreads, smem, st>>>(hyp, ndim, d, P, Np, Xq, wq, Nq, nullptr, out);
   return cudaGetLastError();
 }
 

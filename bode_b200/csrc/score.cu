@@ -4,7 +4,7 @@
 // (get_params_2 :391-402, predict / kern.K inside GPy, xik _core.py:86-92), and the log / mean / var / argmax of
 // mcmc_kld + optimize (:492, :659).  Per (candidate x, hyper-sample s):
 //     k   = K_ARD-RBF(X, x; theta_s)            (K2, phase A: GEMM-form distance on the tensor pipe + exp2, never leaves smem)
-//     xi  = xik(x)                               (K2, closed form, 2d erf)
+//     xi  = xik(x)                               (k_xi: even Chebyshev series of the d factors, erf fallback)
 //     t   = L_s^-1 k ; sigma_x = ss - t.t        (K3, phase B: FP64 tensor-core DMMA.8x8x4 against the tiled L^-1)
 //     v   = xi - w_s.k                           (K3, folded into phase A)
 //     EKLD = log(sqrt(s1)/sqrt(s2)) + s2/(2 s1) + (v^2/s1/(sigma_x+noise))*0.5 - 0.5 ; logk = log(EKLD)   (K4)
@@ -14,9 +14,10 @@
 // exponential on the FP64 pipe), phase B (each warp owns up to RT row tiles x CT column tiles of T = L^-1 Kc as DMMA
 // accumulators; L^-1 streams through a shared-memory ring filled with 1-D bulk copies (TMA, cp.async.bulk + mbarrier)
 // by a rotating duty warp), and a short combine that writes sigma_x and v.  The column groups of a CTA run these
-// phases as independent pipelines (their own named barrier).  k_ekld turns those into log EKLD (K4),
-// k_reduce sums over s sequentially (deterministic, independent of how candidates were tiled or sharded across GPUs)
-// and does the block argmax, k_final_argmax picks the winner.
+// phases as independent pipelines (their own named barrier).  xik(x) comes in through the S x Nd plane (k_xi, launched
+// before this kernel; in quadrature mode k_rowmean's estimate) and the combine overwrites it with log EKLD (K4).
+// k_reduce sums over s sequentially (deterministic, independent of how candidates were tiled or sharded across GPUs),
+// does the block argmax, and its last block to finish picks the winner.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -25,6 +26,7 @@
 #include "layout.h"
 #include "rbf.h"
 #include "score_args.h"
+#include "tuning.h"
 
 namespace bode {
 
@@ -90,6 +92,14 @@ __device__ __forceinline__ void dmma884_ordered(double& c0, double& c1, double a
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
 }
+// shared-memory counter increment with acquire-release semantics (the plain atomicAdd is relaxed)
+__device__ __forceinline__ int atom_add_acq_rel_smem(int* p, int v) {
+  int old;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.s32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+  return old;
+}
+// order this thread's (acquired) view of generic-proxy accesses to shared memory before a following async-proxy (TMA) access
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 template <int NT>
 __device__ __forceinline__ void compute_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
 // one lane of a converged warp (no thread-id arithmetic, no S2R in hot loops)
@@ -366,6 +376,7 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
     mbar_init(aux_full, 1);
     mbar_init(stagger, RG * ((CG + 1) / 2));
     aux_cnt[0] = 0;
+    if (blockIdx.x == 0) *a.done_counter = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int q = tid; q <= nchunks; q += kThreads) {
@@ -454,8 +465,15 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
     long long* tsa = (ts_on && ls < 16) ? &g_ta[((ts_item * 16 + warp) * 16 + ls) * 4] : nullptr;
 #endif
     if (CG > 1 && ls == 0 && (cg & 1) && a.stagger) mbar_wait(stagger, 0);  // opt-in: odd groups one phase A behind
-    double ss = 0;
-    if (tg < GC) ss = auxs[C_SS];
+    // combine threads: the sample's constants (the aux block is recycled after phase A) and this candidate's xi,
+    // fetched now so that its global-memory latency hides behind phases A and B
+    double ss = 0, noise = 0, sigma1 = 0, xi = 0;
+    if (tg < GC) {
+      ss = auxs[C_SS];
+      noise = auxs[C_NOISE];
+      sigma1 = auxs[C_SIGMA1];
+      if (a.mode != kModeVariance && c0 + cbase + tg < a.Nd) xi = a.xi[(size_t)(s_begin + ls) * a.Nd + c0 + cbase + tg];
+    }
     if (!((a.debug_skip & 1) && ls > 0)) {
       // two call sites so that the fragment loads stay address-space specific (LDS vs LDG) instead of generic
       if (a.u_global) {
@@ -472,8 +490,11 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
     __syncwarp();
     if (elect_one()) {
       if (CG > 1 && ls == 0 && !(cg & 1)) mbar_arrive(stagger);
-      const int done = atomicAdd(aux_cnt, 1) + 1;
+      // release this warp's reads of the aux block (ordered before the elected lane by the __syncwarp above), acquire
+      // everybody else's; the last arriver then crosses to the async proxy before the bulk copy overwrites the block
+      const int done = atom_add_acq_rel_smem(aux_cnt, 1) + 1;
       if (done == kWarps * (ls + 1) && ls + 1 < nsamp) {
+        fence_proxy_async_smem();
         mbar_arrive_expect_tx(aux_full, aux_bytes);
         bulk_copy_g2s(smem_u32(auxs), aux_g + (size_t)(ls + 1) * L.aux_doubles, aux_bytes, aux_full);
       }
@@ -553,7 +574,7 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
     group_sync();
     TS_STAMP(6);
 
-    // ---- per-candidate combine: sigma_x = ss - |L^-1 k|^2 and w.k (xik and the EKLD itself are evaluated by k_ekld) ----
+    // ---- per-candidate combine (K4): sigma_x = ss - |L^-1 k|^2, v = xik(x) - w.k, closed-form EKLD, log ----
     if (tg < GC) {
       const int cc = cbase + tg;  // this group's candidates
       double tt = red[cc];
@@ -565,8 +586,23 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
       for (int j = 0; j < NRS; j++) wk += pvp[j * C + cc];
       if (c0 + cc < a.Nd) {
         const size_t o = (size_t)(s_begin + ls) * a.Nd + c0 + cc;
-        a.logk[o] = ss - tt;                            // latent predictive variance (GPy predict, full_cov 1x1)
-        if (a.mode != kModeVariance) a.vplane[o] = wk;  // w.k = e_k^T A^-1 k(X, x), the data term of v (_sampler.py:399)
+        const double sigma_x = ss - tt;           // latent predictive variance (GPy predict, full_cov 1x1; _sampler.py:475)
+        if (a.mode == kModeVariance) {
+          a.out[o] = sigma_x;
+        } else {
+          const double v = xi - wk;               // :399  xik(x) - e_k^T A^-1 k(X, x)
+          const double v2 = v * v;                // :401
+          const double kxx = sigma_x + noise;     // :397  predict(include_likelihood=True)
+          const double sigma2 = sigma1 - v2 / kxx;  // :400
+          double kld;
+          if (a.form == kFormLog1p) {
+            kld = -0.5 * log1p(-(v2 / (sigma1 * kxx)));
+          } else {
+            // :480, same operation order as the reference expression
+            kld = ((log(sqrt(sigma1) / sqrt(sigma2)) + (sigma2 / (2.0 * sigma1))) + ((v2 / sigma1) / (sigma_x + noise)) * 0.5) - 0.5;
+          }
+          a.out[o] = log(kld);                    // :492 np.log(kld_j)
+        }
       }
     }
     TS_STAMP(7);
@@ -577,71 +613,49 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
 }
 
 // ----------------------------------------------------------------------------------------------------------------
-// K4: xik(x), v and the closed-form Gaussian EKLD of every (hyper-sample, candidate), in place over the sigma_x plane
-// (xik reference bode/_core.py:86-92; get_params_2 _sampler.py:399; avg_kld_mean :474-481; the log of mcmc_kld :492)
+// xik(x) of every (hyper-sample, candidate) (reference bode/_core.py:86-92), written to the S x Nd plane the scoring
+// kernel reads it back from (and overwrites in place with log EKLD).  Runs BEFORE k_score: the kernel integral is the
+// only transcendental-heavy candidate-side term, and outside the DMMA pipeline it costs a fraction of what it did inside.
 // ----------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_ekld(const char* __restrict__ ws, Layout L, const double* __restrict__ Xd,
-                                              const double* __restrict__ xi_ovr, double* __restrict__ logk,
-                                              const double* __restrict__ wkplane, int S, int64_t Nd, int form, int use_series) {
+__global__ void __launch_bounds__(256) k_xi(const char* __restrict__ ws, Layout L, const double* __restrict__ Xd,
+                                            double* __restrict__ xi_out, int S, int64_t Nd, int use_series) {
   __shared__ double xc[kCkPad * kXcStride];  // Chebyshev series of the xik factors of the current sample (layout.h)
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = c < Nd;
   const int d = L.d;
   for (int s = blockIdx.y; s < S; s += gridDim.y) {
     const double* aux = reinterpret_cast<const double*>(ws + L.off_aux) + (size_t)s * L.aux_doubles;
-    if (!xi_ovr) {
-      __syncthreads();
-      const double* src = reinterpret_cast<const double*>(ws + L.off_xc) + (size_t)s * L.xc_doubles;
-      for (int idx = threadIdx.x; idx < d * kXcStride; idx += blockDim.x) xc[idx] = src[idx];
-      __syncthreads();
-    }
+    __syncthreads();
+    const double* src = reinterpret_cast<const double*>(ws + L.off_xc) + (size_t)s * L.xc_doubles;
+    for (int idx = threadIdx.x; idx < d * kXcStride; idx += blockDim.x) xc[idx] = src[idx];
+    __syncthreads();
     if (!active) continue;
-    const double ss = aux[C_SS], noise = aux[C_NOISE], sigma1 = aux[C_SIGMA1];
-    const size_t o = (size_t)s * Nd + c;
-    double xi;
-    if (xi_ovr) {
-      xi = xi_ovr[o];  // quadrature estimate (k_rowmean)
-    } else {
-      // _core.py:86-92: ss * prod_k sqrt(pi)/sqrt(2) * ell_k * (erf((1-x)/(sqrt2 ell)) - erf((0-x)/(sqrt2 ell))), k ascending;
-      // each factor from its even Chebyshev series (Clenshaw), or from erf where the series did not converge
-      const double* ck = aux + aux_ck();
-      const double* ell = aux + aux_ell();
-      double xf = 1.0;
-      for (int k = 0; k < d; k++) {
-        const double* a = xc + k * kXcStride;
-        const int n = use_series ? (int)a[0] : 0;
-        const double x = Xd[c * d + k];
-        double fk;
-        if (n > 0) {
-          const double u = fma(2.0, x, -1.0);
-          const double w = fma(2.0 * u, u, -1.0), w2 = 2.0 * w;  // w = 2 u^2 - 1
-          double b1 = 0.0, b2 = 0.0;
-          for (int j = n - 1; j >= 1; j--) {
-            const double t = fma(w2, b1, a[1 + j]) - b2;
-            b2 = b1;
-            b1 = t;
-          }
-          fk = fma(w, b1, a[1]) - b2;
-        } else {
-          fk = 1.2533141373155001 * ell[k] * (erf((1.0 - x) * ck[k]) - erf((0.0 - x) * ck[k]));
+    // _core.py:86-92: ss * prod_k sqrt(pi)/sqrt(2) * ell_k * (erf((1-x)/(sqrt2 ell)) - erf((0-x)/(sqrt2 ell))), k ascending;
+    // each factor from its even Chebyshev series (Clenshaw), or from erf where the series did not converge
+    const double* ck = aux + aux_ck();
+    const double* ell = aux + aux_ell();
+    double xf = 1.0;
+    for (int k = 0; k < d; k++) {
+      const double* a = xc + k * kXcStride;
+      const int n = use_series ? (int)a[0] : 0;
+      const double x = Xd[c * d + k];
+      double fk;
+      if (n > 0) {
+        const double u = fma(2.0, x, -1.0);
+        const double w = fma(2.0 * u, u, -1.0), w2 = 2.0 * w;  // w = 2 u^2 - 1
+        double b1 = 0.0, b2 = 0.0;
+        for (int j = n - 1; j >= 1; j--) {
+          const double t = fma(w2, b1, a[1 + j]) - b2;
+          b2 = b1;
+          b1 = t;
         }
-        xf *= fk;
+        fk = fma(w, b1, a[1]) - b2;
+      } else {
+        fk = 1.2533141373155001 * ell[k] * (erf((1.0 - x) * ck[k]) - erf((0.0 - x) * ck[k]));
       }
-      xi = ss * xf;
+      xf *= fk;
     }
-    const double sigma_x = logk[o];
-    const double v = xi - wkplane[o];    // _sampler.py:399
-    const double v2 = v * v;             // :401
-    const double kxx = sigma_x + noise;  // :397 predict(include_likelihood=True)
-    const double sigma2 = sigma1 - v2 / kxx;  // :400
-    double kld;
-    if (form == kFormLog1p) {
-      kld = -0.5 * log1p(-(v2 / (sigma1 * kxx)));
-    } else {
-      // :480, same operation order as the reference expression
-      kld = ((log(sqrt(sigma1) / sqrt(sigma2)) + (sigma2 / (2.0 * sigma1))) + ((v2 / sigma1) / (sigma_x + noise)) * 0.5) - 0.5;
-    }
-    logk[o] = log(kld);  // :492 np.log(kld_j)
+    xi_out[(size_t)s * Nd + c] = aux[C_SS] * xf;
   }
 }
 
@@ -662,7 +676,9 @@ __device__ __forceinline__ bool better(double av, int64_t ai, double bv, int64_t
 
 __global__ void __launch_bounds__(256) k_reduce(const double* __restrict__ logk, int S, int64_t Nd, int64_t idx_offset,
                                                 double* __restrict__ score, double* __restrict__ var,
-                                                double* __restrict__ part_val, int64_t* __restrict__ part_idx) {
+                                                double* __restrict__ part_val, int64_t* __restrict__ part_idx,
+                                                unsigned int* __restrict__ done_counter, double* __restrict__ best,
+                                                int64_t* __restrict__ best_idx) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double bv = -INFINITY;
   int64_t bi = INT64_MAX;
@@ -682,43 +698,46 @@ __global__ void __launch_bounds__(256) k_reduce(const double* __restrict__ logk,
     bv = mean;
     bi = idx_offset + c;
   }
-  for (int o = 16; o > 0; o >>= 1) {
-    const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-    const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
-  }
   __shared__ double sv[8];
   __shared__ int64_t si[8];
-  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
-  __syncthreads();
+  __shared__ bool last;
+  auto block_best = [&]() {  // (bv, bi) of thread 0 = the block's winner
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0)
+      for (int w = 1; w < 8; w++)
+        if (better(sv[w], si[w], bv, bi)) { bv = sv[w]; bi = si[w]; }
+  };
+  block_best();
   if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; w++)
-      if (better(sv[w], si[w], bv, bi)) { bv = sv[w]; bi = si[w]; }
     part_val[blockIdx.x] = bv;
     part_idx[blockIdx.x] = bi;
+    __threadfence();
+    last = atomicAdd(done_counter, 1u) == gridDim.x - 1;
   }
-}
-
-__global__ void __launch_bounds__(256) k_final_argmax(const double* __restrict__ part_val, const int64_t* __restrict__ part_idx,
-                                                      int nparts, double* __restrict__ best, int64_t* __restrict__ best_idx) {
-  double bv = -INFINITY;
-  int64_t bi = INT64_MAX;
-  for (int i = threadIdx.x; i < nparts; i += blockDim.x)
-    if (better(part_val[i], part_idx[i], bv, bi)) { bv = part_val[i]; bi = part_idx[i]; }
-  for (int o = 16; o > 0; o >>= 1) {
-    const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-    const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
-  }
-  __shared__ double sv[8];
-  __shared__ int64_t si[8];
-  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
   __syncthreads();
+  if (!last) return;
+  // the last block to finish combines the per-block winners (the comparison is a total order, so the result does not
+  // depend on which block runs this or in which order the partials are visited)
+  __threadfence();
+  bv = -INFINITY;
+  bi = INT64_MAX;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+    const double pv_ = __ldcg(part_val + i);
+    const int64_t pi_ = __ldcg(part_idx + i);
+    if (better(pv_, pi_, bv, bi)) { bv = pv_; bi = pi_; }
+  }
+  __syncthreads();
+  block_best();
   if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; w++)
-      if (better(sv[w], si[w], bv, bi)) { bv = sv[w]; bi = si[w]; }
     best[0] = bv;
     best_idx[0] = bi;
+    *done_counter = 0u;  // ready for the next call on this scratch buffer
   }
 }
 
@@ -782,7 +801,7 @@ static int plan_chunks(const Layout& L, size_t smem_limit, size_t chunk_max, Sco
   P->chunk_max = (int)chunk_max;
   const int nthreads = 32 * P->rg * P->cg;
   int max_stages = 2, u_global = 0;  // two stages measured best (deeper rings mean smaller chunks, more transitions)
-  if (const char* sg = getenv("BODE_STAGES")) max_stages = atoi(sg) < 2 ? 2 : (atoi(sg) > kMaxStages ? kMaxStages : atoi(sg));
+  if (tuning().stages > 0) max_stages = tuning().stages < 2 ? 2 : (tuning().stages > kMaxStages ? kMaxStages : tuning().stages);
   int stages = max_stages;
   while (stages >= 2 && score_smem_bytes(L, C, P->rg, nthreads, stages, (int)chunk_max, nch, 0) > smem_limit) stages--;
   if (stages < 2) {  // large n: leave the prescaled observations in global memory (read through L1/L2 in phase A)
@@ -802,8 +821,8 @@ static int plan_chunks(const Layout& L, size_t smem_limit, size_t chunk_max, Sco
 static int plan_variant(const Layout& L, size_t smem_limit, ScorePlan* P) {
   P->C = P->cg * P->ct * 8;
   const size_t pair0_doubles = (size_t)L.nrt * 64;
-  if (const char* ck = getenv("BODE_CHUNK_KB")) {  // tuning knob
-    size_t cm = (size_t)atoi(ck) * 128;
+  if (tuning().chunk_kb > 0) {  // tuning knob
+    size_t cm = (size_t)tuning().chunk_kb * 128;
     return plan_chunks(L, smem_limit, cm < pair0_doubles ? pair0_doubles : cm, P);
   }
   // Every chunk transition costs each warp ~450 cycles of barrier bookkeeping and two ring stages measured best, so:
@@ -842,8 +861,7 @@ int plan_score(const Layout& L, int64_t Nd, int sm_count, size_t smem_optin, Sco
   const int nrt = L.nrt;
   // BODE_SCORE_VARIANT=<id> forces one configuration (tuning knob); the default order is the measured
   // preference: 8 warps with 32 accumulator tiles each (255 registers) beat 16 warps with 16 tiles (128 registers)
-  const char* env = getenv("BODE_SCORE_VARIANT");
-  const int forced = env ? atoi(env) : -1;
+  const int forced = tuning().score_variant;
   struct Cand { int variant, rg, cg, rt, ct; size_t limit; bool only_forced; };
   const Cand cands[] = {
       {3, 4, 2, 8, 2, (228 * 1024) / 2 - 1024, true},  // two CTAs per SM, 32 candidates each (slower: L^-1 is streamed twice)
@@ -868,8 +886,7 @@ int plan_score(const Layout& L, int64_t Nd, int sm_count, size_t smem_optin, Sco
   // work items: (tile, sample chunk); aim for >= 16 waves of CTAs, keep at least 4 samples per item when possible
   const int64_t ntiles = (Nd + C - 1) / C;
   int sc = L.S;
-  int waves = 80;
-  if (const char* wv = getenv("BODE_WAVES")) waves = atoi(wv);  // tuning knob
+  const int waves = tuning().waves > 0 ? tuning().waves : 80;  // tuning knob
   const int64_t target = (int64_t)waves * sm_count;
   while (sc > 4 && ntiles * ((L.S + sc - 1) / sc) < target) sc = (sc + 1) / 2;
   if (ntiles * ((L.S + sc - 1) / sc) < sm_count) {
@@ -883,8 +900,17 @@ int plan_score(const Layout& L, int64_t Nd, int sm_count, size_t smem_optin, Sco
 
 template <int RG, int CG, int RT, int CT>
 static cudaError_t launch_one(const ScoreArgs& a, const ScorePlan& P, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(k_score<RG, CG, RT, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem);
+  static thread_local int attr_dev = -1;
+  static thread_local size_t attr_smem = 0;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
+  if (dev != attr_dev || P.smem > attr_smem) {  // opt in to the large dynamic shared memory once per device / size
+    e = cudaFuncSetAttribute(k_score<RG, CG, RT, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem);
+    if (e != cudaSuccess) return e;
+    attr_dev = dev;
+    attr_smem = P.smem;
+  }
   k_score<RG, CG, RT, CT><<<(unsigned)P.nitems, 32 * RG * CG, P.smem, st>>>(a);
   return cudaGetLastError();
 }
@@ -900,22 +926,17 @@ cudaError_t launch_score(const ScoreArgs& a, const ScorePlan& P, cudaStream_t st
   return launch_one<8, 2, 16, 1>(a, P, st);
 }
 
-cudaError_t launch_ekld(const void* ws, const Layout& L, const double* Xd, const double* xi_ovr, double* logk,
-                        const double* wkplane, int S, int64_t Nd, int form, cudaStream_t st) {
+cudaError_t launch_xi(const void* ws, const Layout& L, const double* Xd, double* xi_out, int S, int64_t Nd, cudaStream_t st) {
   const dim3 grid((unsigned)((Nd + 255) / 256), (unsigned)(S < 65535 ? S : 65535));
-  const char* sv = getenv("BODE_XIK_SERIES");  // developer knob: 0 = evaluate every xik factor with erf
-  const int use_series = !(sv && atoi(sv) == 0);
-  k_ekld<<<grid, 256, 0, st>>>(static_cast<const char*>(ws), L, Xd, xi_ovr, logk, wkplane, S, Nd, form, use_series);
+  k_xi<<<grid, 256, 0, st>>>(static_cast<const char*>(ws), L, Xd, xi_out, S, Nd, tuning().xik_series);
   return cudaGetLastError();
 }
 
 cudaError_t launch_reduce(const double* logk, int S, int64_t Nd, int64_t idx_offset, double* score, double* var,
-                          double* part_val, int64_t* part_idx, double* best, int64_t* best_idx, cudaStream_t st) {
+                          double* part_val, int64_t* part_idx, unsigned int* done_counter, double* best, int64_t* best_idx,
+                          cudaStream_t st) {
   const int nb = (int)((Nd + 255) / 256);
-  k_reduce<<<nb, 256, 0, st>>>(logk, S, Nd, idx_offset, score, var, part_val, part_idx);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  k_final_argmax<<<1, 256, 0, st>>>(part_val, part_idx, nb, best, best_idx);
+  k_reduce<<<nb, 256, 0, st>>>(logk, S, Nd, idx_offset, score, var, part_val, part_idx, done_counter, best, best_idx);
   return cudaGetLastError();
 }
 

@@ -19,8 +19,10 @@ struct ScoreArgs {
   Layout L;
   const double* Xd;  // Nd * d
   int64_t Nd;
-  double* logk;      // S * Nd: sigma_x out of the scoring kernel, log EKLD after k_ekld
-  double* vplane;    // S * Nd: w.k = e_k^T A^-1 k(X, x) out of the scoring kernel (EKLD mode); k_ekld forms v = xik(x) - w.k
+  const double* xi;  // S * Nd: xik(x) per (hyper-sample, candidate) (k_xi, or the quadrature estimate of k_rowmean); EKLD mode only
+  double* out;       // S * Nd: log EKLD (EKLD mode) or sigma_x (variance mode); may alias xi (each element is read, then
+                     // written, by the same thread)
+  unsigned int* done_counter;  // zeroed here for the block-argmax reduction kernel that follows on the same stream
   int S;
   int sc;            // hyper-samples per work item
   int ntiles;        // candidate tiles

@@ -1,0 +1,21 @@
+// Developer tuning knobs (DESIGN.md "Tuning knobs"): environment variables read ONCE per process, not per call.
+// bode_tuning_reload() (C ABI) re-reads them; the tests that force a kernel variant call it after changing the environment.
+#pragma once
+
+namespace bode {
+
+struct Tuning {
+  int score_variant;  // BODE_SCORE_VARIANT  (-1: planner's choice)
+  int chunk_kb;       // BODE_CHUNK_KB       (0: balanced chunks)
+  int waves;          // BODE_WAVES          (target CTA waves of the scoring kernel)
+  int stages;         // BODE_STAGES         (ring stages, >= 2)
+  int debug_skip;     // BODE_DEBUG_SKIP     (timing decomposition only)
+  int stagger;        // BODE_STAGGER
+  int xik_series;     // BODE_XIK_SERIES     (0: evaluate every xik factor with erf)
+  int prep_split;     // BODE_PREP_SPLIT     (CTAs per hyper-sample in the prepare kernel; 0: planner's choice)
+};
+
+const Tuning& tuning();
+void tuning_reload();
+
+}  // namespace bode

@@ -47,18 +47,22 @@ def combine_argmax(vals, idxs):
     return best_v, best_i
 
 
+def pack_record(best_val, best_idx):
+    """(float64 value, int64 index) -> int64[2] tensor: the 16-byte record the ranks exchange."""
+    return torch.cat([best_val.reshape(1).to(torch.float64).view(torch.int64), best_idx.reshape(1).to(torch.int64)])
+
+
 def exchange_best(best_val, best_idx, group=None):
-    """all_gather the 16-byte (value, index) record of every rank and combine.  Tensors live on the caller's
-    device (CUDA with NCCL; CPU with gloo in the tests)."""
+    """torch.distributed form of the exchange (gloo on CPU in the tests; the GPU path uses the C-ABI
+    ``bode_ekld_argmax_nccl`` through ``EkldEngine.exchange_best``): ONE all_gather of the packed 16-byte record, one
+    copy to the host, np.argmax semantics."""
     import torch.distributed as dist
     ws = dist.get_world_size(group)
-    v = best_val.reshape(1).to(torch.float64)
-    i = best_idx.reshape(1).to(torch.int64)
-    vs = [torch.empty_like(v) for _ in range(ws)]
-    is_ = [torch.empty_like(i) for _ in range(ws)]
-    dist.all_gather(vs, v, group=group)
-    dist.all_gather(is_, i, group=group)
-    return combine_argmax(torch.cat(vs).cpu(), torch.cat(is_).cpu())
+    rec = pack_record(best_val, best_idx)
+    out = torch.empty(2 * ws, dtype=torch.int64, device=rec.device)
+    dist.all_gather_into_tensor(out, rec, group=group)
+    host = out.cpu()
+    return combine_argmax(host[0::2].contiguous().view(torch.float64), host[1::2].contiguous())
 
 
 def gather_rows(local, n_total, group=None):
@@ -73,33 +77,60 @@ def gather_rows(local, n_total, group=None):
     return torch.cat(out)[:n_total]
 
 
-def sharded_score(engine, X_design, form=0, group=None, want_scores=True):
+def sharded_score(engine, X_design, form=0, group=None, want_scores=True, want_var=True):
     """Score ``X_design`` (host array, identical on every rank) on this rank's shard and combine across ranks.
 
-    Returns dict(score (Nd,) NumPy or None, var, idx_best (global), best).  Works unsharded when
-    torch.distributed is not initialised.
+    Shards only when a process group is passed explicitly (``torch.distributed.group.WORLD`` for the default one): a
+    caller that merely runs inside an initialised job is not silently split.  Returns dict(score (Nd,) NumPy or None,
+    var, idx_best (global), best).
     """
     import torch.distributed as dist
     Xd = np.ascontiguousarray(X_design, dtype=np.float64)
     Nd = Xd.shape[0]
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        r = engine.score(Xd, form=form)
-        return dict(score=r["score"].cpu().numpy(), var=r["var"].cpu().numpy(), idx_best=int(r["best_idx"].item()),
-                    best=float(r["best"].item()))
+    if group is None or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        r = engine.score(Xd, form=form, want_var=want_var)
+        return dict(score=r["score"].cpu().numpy(), var=r["var"].cpu().numpy() if want_var else None,
+                    idx_best=int(r["best_idx"].item()), best=float(r["best"].item()))
     ws, rank = dist.get_world_size(group), dist.get_rank(group)
     lo, hi = shard_bounds(Nd, ws, rank)
     dev = engine.device
+    use_capi = getattr(engine, "_comm", None) is not None  # EkldEngine.init_nccl(): C-ABI exchange on the compute stream
     if hi > lo:
-        r = engine.score(Xd[lo:hi], idx_offset=lo, form=form)
-        bv, bi, sc, vr = r["best"], r["best_idx"], r["score"], r["var"]
+        r = engine.score(Xd[lo:hi], idx_offset=lo, form=form, want_var=want_var)
+        bv, bi, sc, vr, rec = r["best"], r["best_idx"], r["score"], r["var"], r.get("rec")
     else:
         bv = torch.full((1,), float("-inf"), dtype=torch.float64, device=dev)
         bi = torch.full((1,), -1, dtype=torch.int64, device=dev)
         sc = torch.empty(0, dtype=torch.float64, device=dev)
         vr = torch.empty(0, dtype=torch.float64, device=dev)
-    best, idx = exchange_best(bv, bi, group)
+        rec = None
+    best, idx = engine.exchange_best(rec) if use_capi else exchange_best(bv, bi, group)
     out = dict(idx_best=int(idx), best=float(best), score=None, var=None)
     if want_scores:
         out["score"] = gather_rows(sc, Nd, group).cpu().numpy()
-        out["var"] = gather_rows(vr, Nd, group).cpu().numpy()
+        if want_var and vr is not None:
+            out["var"] = gather_rows(vr, Nd, group).cpu().numpy()
     return out
+
+
+def broadcast_array(a, shape_hint=None, group=None, src=0, device=None):
+    """Rank ``src``'s float64 array on every rank (host MCMC, LHS designs and noisy objective values are drawn on one
+    rank only so that the ranks of a sharded ``KLSampler.optimize`` can never diverge)."""
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    dev = device if (device is not None and dist.get_backend(group) == "nccl") else torch.device("cpu")
+    gsrc = dist.get_global_rank(group, src) if group is not None and group is not dist.group.WORLD else src
+    if rank == src:
+        arr = np.ascontiguousarray(a, dtype=np.float64)
+        meta = torch.tensor([arr.ndim] + list(arr.shape) + [0] * (7 - arr.ndim), dtype=torch.int64, device=dev)
+    else:
+        meta = torch.zeros(8, dtype=torch.int64, device=dev)
+    dist.broadcast(meta, src=gsrc, group=group)
+    m = meta.cpu().tolist()
+    shape = tuple(m[1:1 + m[0]])
+    if rank == src:
+        t = torch.from_numpy(arr).to(dev)
+    else:
+        t = torch.empty(shape, dtype=torch.float64, device=dev)
+    dist.broadcast(t, src=gsrc, group=group)
+    return t.cpu().numpy()

@@ -38,6 +38,52 @@ class EkldEngine:
         self.quad = None
         self._ndim = 0
         self._prepared = False
+        self._comm = None          # our own NCCL communicator (init_nccl), world size / rank
+        self._world = 1
+        self._rank = 0
+        self._gathered = None
+        self.jitter_used = None    # per-sample jitter of the last prepare() when jitchol retries were needed
+
+    # ---- multi-GPU argmax exchange ------------------------------------------------------------------------
+    def init_nccl(self, group=None):
+        """Create the communicator ``bode_ekld_argmax_nccl`` runs on: rank 0 draws an ncclUniqueId, torch.distributed
+        (the caller's process group) carries its 128 bytes to the other ranks.  One communicator per engine."""
+        import torch.distributed as tdist
+        world, rank = tdist.get_world_size(group), tdist.get_rank(group)
+        with torch.cuda.device(self.device):
+            uid = torch.zeros(128, dtype=torch.uint8)
+            if rank == 0:
+                buf = (ctypes.c_ubyte * 128)()
+                _ext.check(self.lib.bode_nccl_unique_id(buf))
+                uid = torch.tensor(list(buf), dtype=torch.uint8)
+            backend = tdist.get_backend(group)
+            t = uid.to(self.device) if backend == "nccl" else uid
+            tdist.broadcast(t, src=tdist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            raw = bytes(t.cpu().tolist())
+            comm = ctypes.c_void_p()
+            _ext.check(self.lib.bode_nccl_comm_create(ctypes.c_char_p(raw), world, rank, ctypes.byref(comm)))
+            self._comm, self._world, self._rank = comm, world, rank
+            self._gathered = torch.empty(2 * world, dtype=torch.int64, device=self.device)
+        return self
+
+    def close_nccl(self):
+        if self._comm is not None:
+            torch.cuda.synchronize(self.device)
+            self.lib.bode_nccl_comm_destroy(self._comm)
+            self._comm = None
+
+    def exchange_best(self, rec):
+        """All ranks: one 16-byte ncclAllGather of the packed (best, idx) record on the compute stream, ONE device->host
+        copy, np.argmax semantics on the host.  ``rec``: the int64[2] tensor of ``score()['rec']`` (or None for a rank
+        without candidates)."""
+        if self._comm is None:
+            raise RuntimeError("call init_nccl() first")
+        with torch.cuda.device(self.device):
+            if rec is None:
+                rec = torch.tensor([0, -1], dtype=torch.int64, device=self.device)
+            _ext.check(self.lib.bode_ekld_argmax_nccl(self._comm, _ptr(rec), _ptr(self._gathered), self._stream()))
+            host = self._gathered.cpu().numpy()
+        return _ext.argmax_combine(host)
 
     # ---- helpers -------------------------------------------------------------------------------------------
     def _dev(self, a, shape=None):
@@ -60,11 +106,15 @@ class EkldEngine:
         return t
 
     # ---- K1 ------------------------------------------------------------------------------------------------
-    def prepare(self, X, Y, hyp, nugget_var, jitter=GPY_JITTER, quad=None):
+    def prepare(self, X, Y, hyp, nugget_var, jitter=GPY_JITTER, quad=None, jitchol_retries=0):
         """Factorise every hyper-sample (``bode_ekld_prepare_dev``).  hyp: (S, d+1) or (S, d+2) reference layout.
 
         quad=(X_quad, weights|None) switches to quadrature mode: the kernel integrals xik / bk are replaced by
-        (weighted) means over the quadrature points, here and in the following ``score`` calls."""
+        (weighted) means over the quadrature points, here and in the following ``score`` calls.
+
+        jitchol_retries > 0 mirrors GPy's ``jitchol`` (what ``make_mcmc_model`` does implicitly, ``_sampler.py:453``): a
+        hyper-sample whose Cholesky fails is re-factorised with an extra ``mean(diag) * 1e-6 * 10^k``, k = 0.. on its
+        diagonal (the healthy samples keep their bits); costs one device->host read of ``info`` per call."""
         with torch.cuda.device(self.device):
             Xd = self._dev(X)
             n, d = Xd.shape
@@ -105,6 +155,24 @@ class EkldEngine:
             self._ndim = ndim
             self._prepared = True
             self._keep = (Xd, Yd, H)  # keep inputs alive until the stream has consumed them
+            self.jitter_used = None
+            if jitchol_retries > 0 and quad is None:
+                info = self.info.cpu().numpy()
+                if (info > 0).any():
+                    noise = (H[:, -1] ** 2).cpu().numpy() if ndim == d + 2 else np.full(S, float(nugget_var))
+                    diag = H[:, 0].cpu().numpy() + noise + jitter
+                    jit = np.full(S, float(jitter))
+                    for k in range(int(jitchol_retries)):
+                        bad = info > 0
+                        if not bad.any():
+                            break
+                        jit[bad] = jitter + diag[bad] * 1e-6 * 10.0 ** k
+                        J = self._dev(jit)
+                        _ext.check(self.lib.bode_ekld_prepare_jitter_dev(_ptr(Xd), _ptr(Yd), _ptr(H), n, d, S, ndim,
+                                                                         float(nugget_var), _ptr(J), _ptr(self.ws),
+                                                                         self.ws.numel(), _ptr(self.info), self._stream()))
+                        info = self.info.cpu().numpy()
+                    self.jitter_used = jit
         return self.info
 
     def loglik(self, X, Y, hyp, nugget_var, jitter=GPY_JITTER):
@@ -156,7 +224,8 @@ class EkldEngine:
     # ---- K2-K4 ---------------------------------------------------------------------------------------------
     def score(self, X_design, idx_offset=0, form=_ext.BODE_FORM_REFERENCE, want_var=True, timed=False, events=None):
         """Score every row of X_design (device or host array).  Returns device tensors:
-        dict(score (Nd,), var (Nd,)|None, logk (S, Nd), best (1,), best_idx (1,) int64)."""
+        dict(score (Nd,), var (Nd,)|None, logk (S, Nd), best (1,), best_idx (1,) int64, rec int64[2] = the packed
+        16-byte (best, best_idx) record).  ``logk`` is a view of an engine-owned buffer, valid until the next call."""
         if not self._prepared:
             raise RuntimeError("call prepare() first")
         with torch.cuda.device(self.device):
@@ -169,9 +238,9 @@ class EkldEngine:
             logk = self._buf("logk", self.S * Nd, torch.float64)[: self.S * Nd].view(self.S, Nd)
             score = torch.empty(Nd, dtype=torch.float64, device=self.device)
             var = torch.empty(Nd, dtype=torch.float64, device=self.device) if want_var else None
-            best = torch.empty(1, dtype=torch.float64, device=self.device)
-            best_idx = torch.empty(1, dtype=torch.int64, device=self.device)
-            scr = self._buf("scratch", 256 + self.lib.bode_ekld_score_scratch_bytes(Nd, self.S), torch.uint8)
+            rec = torch.empty(2, dtype=torch.int64, device=self.device)  # packed {float64 best, int64 best_idx}
+            best, best_idx = rec[:1].view(torch.float64), rec[1:]
+            scr = self._buf("scratch", 256 + self.lib.bode_ekld_score_scratch_bytes(Nd, 0), torch.uint8)
             args = [_ptr(self.ws), self.n, self.d, self.S, _ptr(Xd), Nd, int(idx_offset), int(form), _ptr(logk),
                     _ptr(score), _ptr(var), _ptr(best), _ptr(best_idx), _ptr(scr), self._stream()]
             if self.quad is not None:
@@ -182,7 +251,7 @@ class EkldEngine:
                                                              _ptr(wq), Nq, _ptr(xi), _ptr(logk), _ptr(score), _ptr(var),
                                                              _ptr(best), _ptr(best_idx), _ptr(scr), self._stream()))
                 self._keep_x = Xd
-                return dict(score=score, var=var, logk=logk, best=best, best_idx=best_idx, xi=xi)
+                return dict(score=score, var=var, logk=logk, best=best, best_idx=best_idx, rec=rec, xi=xi)
             if events is not None:
                 # (start, stop) torch.cuda.Event pair recorded around the scoring kernel, no synchronisation
                 _ext.check(self.lib.bode_ekld_score_dev_events(*args, ctypes.c_void_p(events[0].cuda_event),
@@ -194,7 +263,7 @@ class EkldEngine:
             else:
                 _ext.check(self.lib.bode_ekld_score_dev(*args))
             self._keep_x = Xd
-        return dict(score=score, var=var, logk=logk, best=best, best_idx=best_idx)
+        return dict(score=score, var=var, logk=logk, best=best, best_idx=best_idx, rec=rec)
 
     def us_variance(self, X_grid, idx_offset=0):
         """Uncertainty-sampling comparator (``_sampler.py:506-514``): mean_s latent predictive variance + argmax."""
@@ -209,7 +278,7 @@ class EkldEngine:
             pv = torch.empty(Ng, dtype=torch.float64, device=self.device)
             best = torch.empty(1, dtype=torch.float64, device=self.device)
             best_idx = torch.empty(1, dtype=torch.int64, device=self.device)
-            scr = self._buf("scratch", self.lib.bode_ekld_score_scratch_bytes(Ng, self.S), torch.uint8)
+            scr = self._buf("scratch", 256 + self.lib.bode_ekld_score_scratch_bytes(Ng, 0), torch.uint8)
             _ext.check(self.lib.bode_us_variance_dev(_ptr(self.ws), self.n, self.d, self.S, _ptr(Xg), Ng, int(idx_offset),
                                                      _ptr(sigx), _ptr(pv), _ptr(best), _ptr(best_idx), _ptr(scr),
                                                      self._stream()))

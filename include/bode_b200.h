@@ -37,7 +37,8 @@ typedef enum bode_status {
   BODE_ERR_UNSUPPORTED = -2, /* n > BODE_MAX_N or d > BODE_MAX_D */
   BODE_ERR_WORKSPACE = -3,   /* workspace too small / misaligned */
   BODE_ERR_CUDA = -4,        /* CUDA runtime error (see bode_last_cuda_error) */
-  BODE_ERR_NOT_PD = -5       /* host entry points only: a Cholesky pivot was non-positive (info[s] > 0) */
+  BODE_ERR_NOT_PD = -5,      /* host entry points only: a Cholesky pivot was non-positive (info[s] > 0) */
+  BODE_ERR_NCCL = -6         /* libnccl.so.2 not loadable, or an NCCL call failed (see bode_last_cuda_error) */
 } bode_status;
 
 #define BODE_MAX_N 1024 /* observations */
@@ -51,6 +52,10 @@ typedef enum bode_status {
 const char* bode_version(void);
 const char* bode_strerror(int status);
 const char* bode_last_cuda_error(void);
+
+/* The developer tuning knobs (environment variables BODE_SCORE_VARIANT, BODE_CHUNK_KB, BODE_WAVES, BODE_STAGES,
+ * BODE_XIK_SERIES, ...) are read once when the library is loaded, never on the call path; this re-reads them. */
+int bode_tuning_reload(void);
 
 /* Bytes of device workspace `bode_ekld_prepare_dev` needs for (n observations, d dims, S hyper-samples).
  * Returns 0 if the shape is unsupported. 256-byte alignment required. */
@@ -71,6 +76,13 @@ int bode_ekld_prepare_dev(const double* X, const double* Y, const double* hyp, i
                           double nugget_var, double jitter, void* workspace, size_t workspace_bytes, int* info,
                           void* stream);
 
+/* Same with a per-sample diagonal addition jitter_per_sample[S] (device) instead of the scalar: what a caller uses to
+ * mirror GPy's jitchol, which on a failed factorisation retries that model with mean(diag) * 1e-6 * 10^k, k = 0..4
+ * (quadrature mode is not covered by this variant). */
+int bode_ekld_prepare_jitter_dev(const double* X, const double* Y, const double* hyp, int n, int d, int S, int ndim,
+                                 double nugget_var, const double* jitter_per_sample, void* workspace, size_t workspace_bytes,
+                                 int* info, void* stream);
+
 /* Per-sample by-products of prepare, device -> device: out[s*8 + {0..7}] =
  * {variance, noise_var, sigma0, sigma1, mu1, logdet, Y^T A^-1 Y, loglik}. */
 int bode_ekld_sample_terms_dev(const void* workspace, int n, int d, int S, double* out, void* stream);
@@ -80,12 +92,18 @@ int bode_ekld_sample_terms_dev(const void* workspace, int n, int d, int S, doubl
 int bode_ekld_mu_sigma_dev(const void* workspace, int n, int d, int S, double* out, void* stream);
 
 /* K2+K3+K4 -- dense scoring; replaces Nd calls of mcmc_kld (`_sampler.py:483-492`):
- *   logk[s*Nd + c] = log EKLD_s(X_design[c])                    (always written; caller-provided S*Nd doubles)
- *   score[c] = (1/S) sum_s logk[s][c]  (sequential in s),  var[c] = (1/S) sum_s (logk[s][c]-score[c])^2 (nullable)
+ *   score[c] = (1/S) sum_s log EKLD_s(X_design[c])  (sequential in s),
+ *   var[c] = (1/S) sum_s (log EKLD_s - score[c])^2  (nullable),
  *   best[0] = max score (NaN counts as largest, like np.argmax), best_idx[0] = idx_offset + first index attaining it.
+ *   logk[s*Nd + c] = log EKLD_s(X_design[c]) -- NULLABLE: pass S*Nd doubles only if the per-sample matrix is wanted (the
+ *   `kld_j` of `:489-491`); with NULL the one S x Nd plane the kernels need lives in `scratch`.
+ * Three launches: k_xi (xik(x) of every (sample, candidate) into the plane), k_score (cross-covariance, L^-1 contraction
+ * on the FP64 tensor pipe and the fused EKLD epilogue, in place over the plane), k_reduce (mean / var over samples, block
+ * argmax, final argmax by the last block to finish).
  * `idx_offset` is the global index of X_design[0] (multi-GPU candidate sharding).
- * `scratch` needs bode_ekld_score_scratch_bytes(Nd, S) bytes (argmax partials and the S*Nd plane of
- * v = Cov(Q, f(x) | data) that the scoring kernel hands to the EKLD kernel). */
+ * `scratch`: bode_ekld_score_scratch_bytes(Nd, S) bytes when logk is NULL, bode_ekld_score_scratch_bytes(Nd, 0) when logk
+ * is given (argmax partials only); 256-byte aligned.  `best` and `best_idx` may point at the two halves of one 16-byte
+ * record (what bode_ekld_argmax_nccl exchanges). */
 size_t bode_ekld_score_scratch_bytes(int64_t Nd, int S);
 int bode_ekld_score_dev(const void* workspace, int n, int d, int S, const double* X_design, int64_t Nd,
                         int64_t idx_offset, int form, double* logk, double* score, double* var, double* best,
@@ -120,8 +138,8 @@ int bode_quad_rowmean_dev(const double* hyp, int S, int ndim, int d, const doubl
 int bode_ekld_prepare_quad_dev(const double* X, const double* Y, const double* hyp, int n, int d, int S, int ndim,
                                double nugget_var, double jitter, const double* Xq, const double* wq, int Nq,
                                void* workspace, size_t workspace_bytes, int* info, void* scratch, void* stream);
-/* bode_ekld_score_dev with xi_q(x) in place of xik(x); xi is an S*Nd scratch (returned filled);
- * scratch >= 256 + bode_ekld_score_scratch_bytes(Nd, S). */
+/* bode_ekld_score_dev with xi_q(x) in place of xik(x); xi is an S*Nd buffer (returned filled); logk nullable as above;
+ * scratch >= 256 + bode_ekld_score_scratch_bytes(Nd, logk ? 0 : S). */
 int bode_ekld_score_quad_dev(const void* workspace, int n, int d, int S, const double* hyp, int ndim,
                              const double* X_design, int64_t Nd, int64_t idx_offset, int form, const double* Xq,
                              const double* wq, int Nq, double* xi, double* logk, double* score, double* var, double* best,
@@ -133,23 +151,50 @@ int bode_us_variance_dev(const void* workspace, int n, int d, int S, const doubl
                          int64_t idx_offset, double* sigx /* S*Ng scratch */, double* pred_var, double* best,
                          int64_t* best_idx, void* scratch, void* stream);
 
-/* Host-buffer convenience wrapper: the call a non-torch caller (or the reference's Python via ctypes) makes.
+/* Host-buffer entry point: the call a non-torch caller (or the reference's Python via ctypes) makes.
  * Copies X, Y, hyp, X_design to the device, runs prepare + score, copies results back, synchronises.
- * score[Nd] required; var[Nd], kld[S*Nd] (EKLD values, not logs), mu_sigma[2], info[S] nullable. */
+ * score[Nd] required; var[Nd], kld[S*Nd] (EKLD values, not logs), mu_sigma[2], info[S] nullable.
+ * Device buffers live in a reusable context and only grow: after the first call of a given size there is no
+ * cudaMalloc / cudaFree on the call path (the sequential design loop calls this once per iteration).
+ * `bode_ekld_score_host` uses a process-wide context; `*_ctx` variants take an explicit one (NULL = the process-wide one).
+ * A context is bound to the CUDA device current at its first use and serialises its callers. */
+typedef struct bode_ctx bode_ctx;
+int bode_ctx_create(bode_ctx** ctx);
+int bode_ctx_destroy(bode_ctx* ctx);
+long long bode_ctx_alloc_count(bode_ctx* ctx); /* cudaMalloc calls made by this context so far */
 int bode_ekld_score_host(const double* X, const double* Y, const double* hyp, int n, int d, int S, int ndim,
                          double nugget_var, double jitter, const double* X_design, int64_t Nd, int form,
                          double* score, double* var, double* kld, int64_t* best_idx, double* mu_sigma, int* info);
+int bode_ekld_score_host_ctx(bode_ctx* ctx, const double* X, const double* Y, const double* hyp, int n, int d, int S, int ndim,
+                             double nugget_var, double jitter, const double* X_design, int64_t Nd, int form,
+                             double* score, double* var, double* kld, int64_t* best_idx, double* mu_sigma, int* info);
 
 /* Batched GP log marginal likelihood for the host MCMC (`lnprob` -> `get_likelihood`, `_sampler.py:221-238`):
  * loglik[s] for each row of hyp; -inf where the Cholesky fails.  Host pointers. */
 int bode_gp_loglik_host(const double* X, const double* Y, const double* hyp, int n, int d, int S, int ndim,
                         double nugget_var, double jitter, double* loglik);
+int bode_gp_loglik_host_ctx(bode_ctx* ctx, const double* X, const double* Y, const double* hyp, int n, int d, int S, int ndim,
+                            double nugget_var, double jitter, double* loglik);
 
 /* Device-pointer form of the same (one launch of the prepare kernel in likelihood-only mode + a gather):
  * loglik[S] device; workspace as for bode_ekld_prepare_dev (its scoring state is NOT valid afterwards). */
 int bode_gp_loglik_dev(const double* X, const double* Y, const double* hyp, int n, int d, int S, int ndim,
                        double nugget_var, double jitter, void* workspace, size_t workspace_bytes, int* info, double* loglik,
                        void* stream);
+
+/* ---- multi-GPU: candidate blocks are independent, the only exchange is the argmax (replaces the
+ * np.argmax of `_sampler.py:659` across ranks).  Each rank's scoring call leaves a 16-byte record {double best;
+ * int64 best_idx} (pass best = rec, best_idx = rec + 8); bode_ekld_argmax_nccl enqueues ONE ncclAllGather of that record
+ * on `stream` (no host synchronisation) into gathered[16 * world] (device); the caller copies those bytes to the host
+ * once and bode_argmax_combine picks the winner with np.argmax semantics (NaN counts as the maximum, ties -> lowest
+ * index; records with idx < 0 are ranks without candidates).  NCCL is resolved at run time (dlopen of libnccl.so.2 --
+ * inside a torch process that is torch's own copy); the communicator is created from a 128-byte ncclUniqueId that rank 0
+ * generates and the caller distributes (torch.distributed broadcast, MPI, a file, ...). */
+int bode_nccl_unique_id(void* id128);
+int bode_nccl_comm_create(const void* id128, int world, int rank, void** comm);
+int bode_nccl_comm_destroy(void* comm);
+int bode_ekld_argmax_nccl(void* comm, const void* best_rec, void* gathered, void* stream);
+int bode_argmax_combine(const void* records_host, int count, double* best, int64_t* best_idx);
 
 /* Host-only: JSON description of the launch plan the scoring entry points would use for this shape on a device with
  * `sm_count` SMs and `smem_optin` bytes of opt-in shared memory per CTA (kernel variant, candidates per CTA, ring

@@ -130,8 +130,12 @@ def test_forced_kernel_variants_agree(ext, variant, n, monkeypatch):
     X, Y, Xd, hyp = cases.make_problem(d, n, S, Nd, seed=900 + n, ell_lo=0.3, ell_hi=0.9)
     base = gpu_score(ext, X, Y, hyp, Xd)
     monkeypatch.setenv("BODE_SCORE_VARIANT", str(variant))
-    forced = gpu_score(ext, X, Y, hyp, Xd)
-    monkeypatch.delenv("BODE_SCORE_VARIANT")
+    ext.reload_tuning()  # the knobs are read once per process, not per call
+    try:
+        forced = gpu_score(ext, X, Y, hyp, Xd)
+    finally:
+        monkeypatch.delenv("BODE_SCORE_VARIANT")
+        ext.reload_tuning()
     assert (forced["info"] == 0).all()
     np.testing.assert_allclose(forced["kld"], base["kld"], rtol=1e-9, atol=1e-15)
     np.testing.assert_allclose(forced["score"], base["score"], rtol=0, atol=1e-9)
@@ -177,8 +181,12 @@ def test_xik_series_matches_erf(ext, d, n, lo, hi, monkeypatch):
     Xd[:3] = [[0.0] * d, [1.0] * d, [0.5] * d]   # the ends and the centre of the symmetric series
     series = gpu_score(ext, X, Y, hyp, Xd)
     monkeypatch.setenv("BODE_XIK_SERIES", "0")
-    direct = gpu_score(ext, X, Y, hyp, Xd)
-    monkeypatch.delenv("BODE_XIK_SERIES")
+    ext.reload_tuning()
+    try:
+        direct = gpu_score(ext, X, Y, hyp, Xd)
+    finally:
+        monkeypatch.delenv("BODE_XIK_SERIES")
+        ext.reload_tuning()
     assert (series["info"] == 0).all()
     np.testing.assert_allclose(series["kld"], direct["kld"], rtol=1e-10, atol=1e-15)
     assert_argmax(series["argmax"], direct["score"])  # (equal up to ties at rounding level)
@@ -282,6 +290,117 @@ def test_not_positive_definite_is_reported(ext):
     assert ei.value.status == -5
     r = ext.ekld_score_host(X, Y, hyp, rng.random((10, 2)), 0.0, jitter=0.0, raise_not_pd=False)
     assert r["info"][0] == 5 and (r["info"] >= 0).all() and np.isnan(r["score"]).all() and r["argmax"] == 0
+
+
+def test_jitchol_retries_like_gpy(engine):
+    """GPy's jitchol (inside make_mcmc_model, `_sampler.py:453`) retries a failed factorisation with mean(diag) * 1e-6 * 10^k
+    on the diagonal; EkldEngine.prepare(jitchol_retries=5) does the same per hyper-sample and leaves healthy samples alone."""
+    rng = np.random.default_rng(0)
+    X = rng.random((6, 2)); X[4] = X[1]
+    Y = rng.random((6, 1)); Y[4] = Y[1]
+    hyp = np.array([[1.0, 0.5, 0.5], [2.0, 0.4, 0.6], [1.5, 0.05, 0.05]])
+    info = engine.prepare(X, Y, hyp, 0.0, jitter=0.0)
+    assert int(info[0]) == 5                         # duplicate row, no nugget, no jitter: pivot 5 is not positive
+    t_plain = engine.sample_terms().cpu().numpy()
+    info = engine.prepare(X, Y, hyp, 0.0, jitter=0.0, jitchol_retries=5)
+    assert (info.cpu().numpy() == 0).all()
+    ju = engine.jitter_used
+    assert ju[0] == pytest.approx(1e-6) and ju[2] == 0.0    # mean(diag) = variance = 1 -> first retry adds 1e-6
+    t = engine.sample_terms().cpu().numpy()
+    assert np.isfinite(t).all()
+    np.testing.assert_array_equal(t[2], t_plain[2])       # the healthy sample keeps its bits
+    sc = engine.score(rng.random((50, 2)))["score"]
+    assert bool((sc == sc).all())
+
+
+def test_host_entry_reuses_its_device_buffers(ext):
+    """`bode_ekld_score_host` keeps its device buffers in a context: 50 calls, no cudaMalloc after the first (ABI hygiene)."""
+    import torch
+    X, Y, Xd, hyp = cases.make_problem(3, 20, 5, 700, seed=9, ell_lo=0.2, ell_hi=0.7)
+    ctx = ext.HostContext()
+    first = ext.ekld_score_host(X, Y, hyp, Xd, 1e-6, want_kld=True, ctx=ctx)
+    n_alloc = ctx.alloc_count()
+    free0 = torch.cuda.mem_get_info()[0]
+    for _ in range(50):
+        r = ext.ekld_score_host(X, Y, hyp, Xd[:500], 1e-6, want_kld=True, ctx=ctx)   # smaller call: buffers only grow
+    assert ctx.alloc_count() == n_alloc and torch.cuda.mem_get_info()[0] == free0
+    np.testing.assert_array_equal(r["score"], first["score"][:500])
+    base = ext.default_ctx_alloc_count()
+    for _ in range(3):
+        ext.ekld_score_host(X, Y, hyp, Xd, 1e-6)
+    after = ext.default_ctx_alloc_count()
+    for _ in range(10):
+        ext.ekld_score_host(X, Y, hyp, Xd, 1e-6)
+    assert ext.default_ctx_alloc_count() == after >= base
+    ctx.close()
+
+
+def test_logk_is_optional_in_the_c_abi(engine, ext):
+    """`bode_ekld_score_dev` with logk = NULL keeps its one S x Nd plane in scratch: same scores, same argmax."""
+    import ctypes
+    import torch
+    X, Y, Xd, hyp = cases.make_problem(4, 30, 6, 900, seed=12, ell_lo=0.2, ell_hi=0.7)
+    engine.prepare(X, Y, hyp, 1e-6)
+    full = engine.score(Xd)
+    lib, dev = engine.lib, engine.device
+    S, Nd = hyp.shape[0], Xd.shape[0]
+    xd = torch.from_numpy(Xd).to(dev)
+    score = torch.empty(Nd, dtype=torch.float64, device=dev)
+    rec = torch.empty(2, dtype=torch.int64, device=dev)
+    scr = torch.empty(lib.bode_ekld_score_scratch_bytes(Nd, S), dtype=torch.uint8, device=dev)
+    assert lib.bode_ekld_score_scratch_bytes(Nd, S) >= 8 * S * Nd > lib.bode_ekld_score_scratch_bytes(Nd, 0)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    ext.check(lib.bode_ekld_score_dev(p(engine.ws), engine.n, engine.d, S, p(xd), Nd, 0, 0, None, p(score), None, p(rec[:1]), p(rec[1:]),
+                                      p(scr), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    assert torch.equal(score, full["score"]) and int(rec[1]) == int(full["best_idx"]) and torch.equal(rec, full["rec"])
+
+
+def _nccl_worker(rank, world, port, payload, q):
+    import torch
+    import torch.distributed as tdist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    tdist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from bode_b200 import dist as bdist
+        from bode_b200.engine import EkldEngine
+        X, Y, Xd, hyp = payload
+        eng = EkldEngine().init_nccl(tdist.group.WORLD)
+        eng.prepare(X, Y, hyp, 1e-6)
+        res = bdist.sharded_score(eng, Xd, group=tdist.group.WORLD)
+        empty = bdist.sharded_score(eng, Xd[:1], group=tdist.group.WORLD)   # rank 1 has no candidates
+        q.put((rank, res["idx_best"], res["best"], res["score"].tolist(), res["var"].tolist(), empty["idx_best"]))
+        eng.close_nccl()
+    finally:
+        tdist.destroy_process_group()
+
+
+def test_two_ranks_over_nccl_match_single_rank_bitwise(engine):
+    """Two processes, one GPU each, candidate blocks sharded, the 16-byte argmax record exchanged by
+    `bode_ekld_argmax_nccl` (C ABI, our own communicator): scores, variance and winner identical to one rank, bit for bit."""
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    X, Y, Xd, hyp = cases.make_problem(6, 60, 8, 3001, seed=44, ell_lo=0.2, ell_hi=0.8)
+    engine.prepare(X, Y, hyp, 1e-6)
+    one = engine.score(Xd)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, (X, Y, Xd, hyp), q)) for r in range(2)]
+    [p.start() for p in procs]
+    out = sorted(q.get(timeout=300) for _ in range(2))
+    [p.join(timeout=120) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    for rank, idx, best, score, var, idx_empty in out:
+        assert idx == int(one["best_idx"].item()) and best == float(one["best"].item())
+        np.testing.assert_array_equal(np.array(score), one["score"].cpu().numpy())
+        np.testing.assert_array_equal(np.array(var), one["var"].cpu().numpy())
+        assert idx_empty == 0
 
 
 def test_invalid_hyperparameters_are_rejected(ext):

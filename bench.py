@@ -352,7 +352,7 @@ def main():
                          "algorithmic_bytes_per_eval": (8 * d + 8) / S + 16},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": 4 * args.steps,  # k_prepare (+ xik series blocks), k_xi, k_score, k_reduce (+ final argmax) per step
+            "gpu_launches": 3 * args.steps,  # k_prepare (+ xik series blocks), k_score, k_ekld_reduce (+ final argmax) per step
             "clocks": clock_info,
             "best_idx": best[1],
         }

@@ -24,7 +24,10 @@ cudaError_t launch_mu_sigma(const void* ws, const Layout& L, double* out, cudaSt
 cudaError_t launch_loglik_gather(const void* ws, const Layout& L, double* out, cudaStream_t st);
 int plan_score(const Layout& L, int64_t Nd, int sm_count, size_t smem_optin, ScorePlan* P);
 cudaError_t launch_score(const ScoreArgs& a, const ScorePlan& P, cudaStream_t st);
-cudaError_t launch_xi(const void* ws, const Layout& L, const double* Xd, double* xi_out, int S, int64_t Nd, cudaStream_t st);
+cudaError_t launch_ekld_reduce(const void* ws, const Layout& L, const double* Xd, const double* xi_ovr, double* sx,
+                               const double* wkplane, int S, int64_t Nd, int64_t idx_offset, int form, int keep_logk,
+                               double* score, double* var, double* part_val, int64_t* part_idx, unsigned int* done_counter,
+                               double* best, int64_t* best_idx, cudaStream_t st);
 cudaError_t launch_reduce(const double* logk, int S, int64_t Nd, int64_t idx_offset, double* score, double* var,
                           double* part_val, int64_t* part_idx, unsigned int* done_counter, double* best, int64_t* best_idx,
                           cudaStream_t st);
@@ -347,9 +350,10 @@ int bode_ekld_mu_sigma_dev(const void* workspace, int n, int d, int S, double* o
   return BODE_OK;
 }
 
-// scratch = [done counter + packed (best, idx) record: 256 B] [block argmax values] [block argmax indices] [S*Nd plane, if S > 0]
+// scratch = [done counter: 256 B] [block argmax values] [block argmax indices] [w.k plane: S*Nd] [sigma_x plane: S*Nd, only
+// when the caller passes no logk buffer]
 static size_t score_partials_bytes(int64_t Nd) {
-  const size_t nb = (size_t)((Nd + 255) / 256);
+  const size_t nb = (size_t)((Nd + 63) / 64);  // an upper bound for both reduction kernels' block counts
   return 256 + align_up(nb * sizeof(double), 256) + align_up(nb * sizeof(int64_t), 256);
 }
 
@@ -373,25 +377,26 @@ static int score_common(const void* workspace, int n, int d, int S, const double
   const Layout L = make_layout(n, d, S);
   if (plan_score(L, Nd, props.sm_count, props.smem_optin, &P) != 0) return BODE_ERR_UNSUPPORTED;
   char* scr = static_cast<char*>(scratch);
-  const size_t nb = (size_t)((Nd + 255) / 256);
+  const size_t nb = (size_t)((Nd + 63) / 64);
   unsigned int* done_counter = reinterpret_cast<unsigned int*>(scr);
   double* part_val = reinterpret_cast<double*>(scr + 256);
   int64_t* part_idx = reinterpret_cast<int64_t*>(scr + 256 + align_up(nb * sizeof(double), 256));
-  // the S x Nd plane: xik(x) in, log EKLD (or sigma_x) out; the caller's logk buffer if given, else the tail of scratch
-  double* plane = logk ? logk : reinterpret_cast<double*>(scr + score_partials_bytes(Nd));
+  // two S x Nd planes between the kernels: w.k (scratch) and sigma_x (the caller's logk buffer if given -- it is turned
+  // into log EKLD in place -- else the second plane of scratch)
+  double* wkp = reinterpret_cast<double*>(scr + score_partials_bytes(Nd));
+  double* sxp = logk ? logk : wkp + (size_t)S * (size_t)Nd;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ScoreArgs a;
   a.ws = workspace; a.L = L; a.Xd = Xd; a.Nd = Nd; a.S = S;
-  a.xi = xi_ovr ? xi_ovr : plane;
+  a.sx = sxp;
+  a.wk = wkp;
   a.done_counter = done_counter;
-  a.out = plane;
   a.sc = P.sc; a.ntiles = P.ntiles; a.form = form; a.mode = mode;
   a.debug_skip = tuning().debug_skip;
   a.stagger = tuning().stagger;
   a.stages = P.stages; a.chunk_max = P.chunk_max; a.nchunks = P.nchunks; a.u_global = P.u_global;
   memcpy(a.chunk_g0, P.chunk_g0, sizeof(a.chunk_g0));
   memcpy(a.tile_id, P.tile_id, sizeof(a.tile_id));
-  if (mode == kModeEkld && !xi_ovr) BODE_CUDA(launch_xi(workspace, L, Xd, plane, S, Nd, st));
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (kernel_ms) {
     BODE_CUDA(cudaEventCreate(&ev0));
@@ -402,7 +407,11 @@ static int score_common(const void* workspace, int n, int d, int S, const double
   BODE_CUDA(launch_score(a, P, st));
   if (ev_stop) BODE_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_stop), st));
   if (kernel_ms) BODE_CUDA(cudaEventRecord(ev1, st));
-  BODE_CUDA(launch_reduce(plane, S, Nd, idx_offset, score, var, part_val, part_idx, done_counter, best, best_idx, st));
+  if (mode == kModeEkld)
+    BODE_CUDA(launch_ekld_reduce(workspace, L, Xd, xi_ovr, sxp, wkp, S, Nd, idx_offset, form, logk != nullptr, score, var, part_val,
+                                 part_idx, done_counter, best, best_idx, st));
+  else
+    BODE_CUDA(launch_reduce(sxp, S, Nd, idx_offset, score, var, part_val, part_idx, done_counter, best, best_idx, st));
   if (kernel_ms) {
     BODE_CUDA(cudaEventSynchronize(ev1));
     BODE_CUDA(cudaEventElapsedTime(kernel_ms, ev0, ev1));
@@ -496,7 +505,7 @@ int bode_ekld_score_host_ctx(bode_ctx* c, const double* X, const double* Y, cons
   BODE_CUDA(c->need(B::kScore, sizeof(double) * Nd));
   BODE_CUDA(c->need(B::kVar, sizeof(double) * Nd));
   BODE_CUDA(c->need(B::kBest, 64));
-  BODE_CUDA(c->need(B::kScr, bode_ekld_score_scratch_bytes(Nd, 0)));
+  BODE_CUDA(c->need(B::kScr, bode_ekld_score_scratch_bytes(Nd, S)));
   BODE_CUDA(c->need(B::kMs, 2 * sizeof(double)));
   cudaStream_t st = c->stream;
   BODE_CUDA(cudaMemcpyAsync(c->b[B::kX].p, X, sizeof(double) * n * d, cudaMemcpyHostToDevice, st));

@@ -14,10 +14,9 @@
 // exponential on the FP64 pipe), phase B (each warp owns up to RT row tiles x CT column tiles of T = L^-1 Kc as DMMA
 // accumulators; L^-1 streams through a shared-memory ring filled with 1-D bulk copies (TMA, cp.async.bulk + mbarrier)
 // by a rotating duty warp), and a short combine that writes sigma_x and v.  The column groups of a CTA run these
-// phases as independent pipelines (their own named barrier).  xik(x) comes in through the S x Nd plane (k_xi, launched
-// before this kernel; in quadrature mode k_rowmean's estimate) and the combine overwrites it with log EKLD (K4).
-// k_reduce sums over s sequentially (deterministic, independent of how candidates were tiled or sharded across GPUs),
-// does the block argmax, and its last block to finish picks the winner.
+// phases as independent pipelines (their own named barrier).  k_ekld_reduce then evaluates xik(x), v and the closed-form
+// EKLD (K4), sums log EKLD over s in hyper-sample order (deterministic, independent of how candidates were tiled or
+// sharded across GPUs), does the block argmax, and its last block to finish picks the winner.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -465,15 +464,8 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
     long long* tsa = (ts_on && ls < 16) ? &g_ta[((ts_item * 16 + warp) * 16 + ls) * 4] : nullptr;
 #endif
     if (CG > 1 && ls == 0 && (cg & 1) && a.stagger) mbar_wait(stagger, 0);  // opt-in: odd groups one phase A behind
-    // combine threads: the sample's constants (the aux block is recycled after phase A) and this candidate's xi,
-    // fetched now so that its global-memory latency hides behind phases A and B
-    double ss = 0, noise = 0, sigma1 = 0, xi = 0;
-    if (tg < GC) {
-      ss = auxs[C_SS];
-      noise = auxs[C_NOISE];
-      sigma1 = auxs[C_SIGMA1];
-      if (a.mode != kModeVariance && c0 + cbase + tg < a.Nd) xi = a.xi[(size_t)(s_begin + ls) * a.Nd + c0 + cbase + tg];
-    }
+    double ss = 0;
+    if (tg < GC) ss = auxs[C_SS];
     if (!((a.debug_skip & 1) && ls > 0)) {
       // two call sites so that the fragment loads stay address-space specific (LDS vs LDG) instead of generic
       if (a.u_global) {
@@ -574,7 +566,9 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
     group_sync();
     TS_STAMP(6);
 
-    // ---- per-candidate combine (K4): sigma_x = ss - |L^-1 k|^2, v = xik(x) - w.k, closed-form EKLD, log ----
+    // ---- per-candidate combine: sigma_x = ss - |L^-1 k|^2 and w.k.  The closed-form EKLD itself (two logs, two square
+    // roots, four divisions: ~2.8k cycles of dependent FP64 latency per candidate) is finished by k_ekld_reduce: evaluated
+    // here it sat on this column group's critical path once per sample and cost k_score 7 % (measured, round 2).
     if (tg < GC) {
       const int cc = cbase + tg;  // this group's candidates
       double tt = red[cc];
@@ -586,23 +580,8 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
       for (int j = 0; j < NRS; j++) wk += pvp[j * C + cc];
       if (c0 + cc < a.Nd) {
         const size_t o = (size_t)(s_begin + ls) * a.Nd + c0 + cc;
-        const double sigma_x = ss - tt;           // latent predictive variance (GPy predict, full_cov 1x1; _sampler.py:475)
-        if (a.mode == kModeVariance) {
-          a.out[o] = sigma_x;
-        } else {
-          const double v = xi - wk;               // :399  xik(x) - e_k^T A^-1 k(X, x)
-          const double v2 = v * v;                // :401
-          const double kxx = sigma_x + noise;     // :397  predict(include_likelihood=True)
-          const double sigma2 = sigma1 - v2 / kxx;  // :400
-          double kld;
-          if (a.form == kFormLog1p) {
-            kld = -0.5 * log1p(-(v2 / (sigma1 * kxx)));
-          } else {
-            // :480, same operation order as the reference expression
-            kld = ((log(sqrt(sigma1) / sqrt(sigma2)) + (sigma2 / (2.0 * sigma1))) + ((v2 / sigma1) / (sigma_x + noise)) * 0.5) - 0.5;
-          }
-          a.out[o] = log(kld);                    // :492 np.log(kld_j)
-        }
+        a.sx[o] = ss - tt;                          // latent predictive variance (GPy predict, full_cov 1x1; _sampler.py:475)
+        if (a.mode != kModeVariance) a.wk[o] = wk;  // w.k = e_k^T A^-1 k(X, x), the data term of v (_sampler.py:399)
       }
     }
     TS_STAMP(7);
@@ -613,55 +592,18 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
 }
 
 // ----------------------------------------------------------------------------------------------------------------
-// xik(x) of every (hyper-sample, candidate) (reference bode/_core.py:86-92), written to the S x Nd plane the scoring
-// kernel reads it back from (and overwrites in place with log EKLD).  Runs BEFORE k_score: the kernel integral is the
-// only transcendental-heavy candidate-side term, and outside the DMMA pipeline it costs a fraction of what it did inside.
+// K4 + reduction, ONE kernel: xik(x), v, the closed-form Gaussian EKLD and its log for every (hyper-sample, candidate),
+// mean / variance over the hyper-samples, block argmax and (last block to finish) the final argmax.
+// (xik reference bode/_core.py:86-92; get_params_2 _sampler.py:399-401; avg_kld_mean :474-481; mcmc_kld :492; argmax :659)
+//
+// Four lanes share a candidate: lane j of the quad evaluates log EKLD for the hyper-samples s = 4i + j (the expensive,
+// independent part), then the quad adds its four values to the running sum in the order s = 4i, 4i+1, 4i+2, 4i+3 --
+// every lane of the quad performs the same additions, so the sum over hyper-samples is exactly the sequential
+// s = 0..S-1 sum the oracle defines, independent of tiling, sharding and launch geometry.
 // ----------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_xi(const char* __restrict__ ws, Layout L, const double* __restrict__ Xd,
-                                            double* __restrict__ xi_out, int S, int64_t Nd, int use_series) {
-  __shared__ double xc[kCkPad * kXcStride];  // Chebyshev series of the xik factors of the current sample (layout.h)
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = c < Nd;
-  const int d = L.d;
-  for (int s = blockIdx.y; s < S; s += gridDim.y) {
-    const double* aux = reinterpret_cast<const double*>(ws + L.off_aux) + (size_t)s * L.aux_doubles;
-    __syncthreads();
-    const double* src = reinterpret_cast<const double*>(ws + L.off_xc) + (size_t)s * L.xc_doubles;
-    for (int idx = threadIdx.x; idx < d * kXcStride; idx += blockDim.x) xc[idx] = src[idx];
-    __syncthreads();
-    if (!active) continue;
-    // _core.py:86-92: ss * prod_k sqrt(pi)/sqrt(2) * ell_k * (erf((1-x)/(sqrt2 ell)) - erf((0-x)/(sqrt2 ell))), k ascending;
-    // each factor from its even Chebyshev series (Clenshaw), or from erf where the series did not converge
-    const double* ck = aux + aux_ck();
-    const double* ell = aux + aux_ell();
-    double xf = 1.0;
-    for (int k = 0; k < d; k++) {
-      const double* a = xc + k * kXcStride;
-      const int n = use_series ? (int)a[0] : 0;
-      const double x = Xd[c * d + k];
-      double fk;
-      if (n > 0) {
-        const double u = fma(2.0, x, -1.0);
-        const double w = fma(2.0 * u, u, -1.0), w2 = 2.0 * w;  // w = 2 u^2 - 1
-        double b1 = 0.0, b2 = 0.0;
-        for (int j = n - 1; j >= 1; j--) {
-          const double t = fma(w2, b1, a[1 + j]) - b2;
-          b2 = b1;
-          b1 = t;
-        }
-        fk = fma(w, b1, a[1]) - b2;
-      } else {
-        fk = 1.2533141373155001 * ell[k] * (erf((1.0 - x) * ck[k]) - erf((0.0 - x) * ck[k]));
-      }
-      xf *= fk;
-    }
-    xi_out[(size_t)s * Nd + c] = aux[C_SS] * xf;
-  }
-}
+constexpr int kErCpq = 2;                 // candidates per quad of lanes (independent dependency chains per thread)
+constexpr int kErCand = 64 * kErCpq;      // candidates per block (256 threads)
 
-// ----------------------------------------------------------------------------------------------------------------
-// Reduction over hyper-samples (sequential in s, like the oracle) + block argmax
-// ----------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool better(double av, int64_t ai, double bv, int64_t bi) {
   // np.argmax semantics: NaN counts as the maximum; ties -> lowest index
   const bool an = isnan(av), bn = isnan(bv);
@@ -674,6 +616,231 @@ __device__ __forceinline__ bool better(double av, int64_t ai, double bv, int64_t
   return ai < bi;
 }
 
+// block winner -> thread 0 (bv, bi); sv / si: shared scratch of 8 entries each
+__device__ __forceinline__ void block_best(double& bv, int64_t& bi, double* sv, int64_t* si) {
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int w = 1; w < 8; w++)
+      if (better(sv[w], si[w], bv, bi)) { bv = sv[w]; bi = si[w]; }
+}
+
+// the last block to finish combines the per-block winners (the comparison is a total order, so the result does not
+// depend on which block runs this or in which order the partials are visited)
+__device__ __forceinline__ void final_argmax(double bv, int64_t bi, double* part_val, int64_t* part_idx,
+                                             unsigned int* done_counter, double* best, int64_t* best_idx, double* sv,
+                                             int64_t* si, bool* last) {
+  if (threadIdx.x == 0) {
+    part_val[blockIdx.x] = bv;
+    part_idx[blockIdx.x] = bi;
+    __threadfence();
+    *last = atomicAdd(done_counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!*last) return;
+  __threadfence();
+  bv = -INFINITY;
+  bi = INT64_MAX;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+    const double pv_ = __ldcg(part_val + i);
+    const int64_t pi_ = __ldcg(part_idx + i);
+    if (better(pv_, pi_, bv, bi)) { bv = pv_; bi = pi_; }
+  }
+  __syncthreads();
+  block_best(bv, bi, sv, si);
+  if (threadIdx.x == 0) {
+    best[0] = bv;
+    best_idx[0] = bi;
+    *done_counter = 0u;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_ekld_reduce(const char* __restrict__ ws, Layout L, const double* __restrict__ Xd,
+                                                     const double* __restrict__ xi_ovr, double* __restrict__ sx,
+                                                     const double* __restrict__ wkplane, int S, int64_t Nd, int64_t idx_offset,
+                                                     int form, int use_series, int keep_logk, double* __restrict__ score,
+                                                     double* __restrict__ var, double* __restrict__ part_val,
+                                                     int64_t* __restrict__ part_idx, unsigned int* __restrict__ done_counter,
+                                                     double* __restrict__ best, int64_t* __restrict__ best_idx) {
+  extern __shared__ __align__(16) double xc[];  // [4][d][kXcStride]: series of the xik factors of the 4 samples in flight
+  __shared__ double cst[4][4];                  // {variance, noise, sigma1} of those samples
+  __shared__ double sv[8];
+  __shared__ int64_t si[8];
+  __shared__ bool last;
+  const int d = L.d;
+  const int sl = threadIdx.x & 3, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int xcs = d * kXcStride;
+  int64_t c[kErCpq];
+  double acc[kErCpq];
+#pragma unroll
+  for (int q = 0; q < kErCpq; q++) {
+    c[q] = (int64_t)blockIdx.x * kErCand + q * 64 + (threadIdx.x >> 2);
+    acc[q] = 0.0;
+  }
+  for (int s0 = 0; s0 < S; s0 += 4) {
+    __syncthreads();
+    if (!xi_ovr) {
+      // only the live part of each series: [n_terms, a_0/2, a_1 .. a_(n-1)]
+      for (int jk = warp; jk < 4 * d; jk += 8) {
+        const int j = jk / d, k = jk - j * d;
+        if (s0 + j < S) {
+          const double* src = reinterpret_cast<const double*>(ws + L.off_xc) + (size_t)(s0 + j) * L.xc_doubles + (size_t)k * kXcStride;
+          const int n = (int)src[0];
+          double* dst = xc + j * xcs + k * kXcStride;
+          if (lane <= n) dst[lane] = src[lane];
+          if (lane + 32 <= n) dst[lane + 32] = src[lane + 32];
+        }
+      }
+    }
+    if (threadIdx.x < 12) {
+      const int j = threadIdx.x / 3, q = threadIdx.x - 3 * j;
+      if (s0 + j < S) {
+        const double* aux = reinterpret_cast<const double*>(ws + L.off_aux) + (size_t)(s0 + j) * L.aux_doubles;
+        cst[j][q] = aux[q == 0 ? C_SS : (q == 1 ? C_NOISE : C_SIGMA1)];
+      }
+    }
+    __syncthreads();
+    const int s = s0 + sl;
+    double lk[kErCpq];
+#pragma unroll
+    for (int q = 0; q < kErCpq; q++) lk[q] = 0.0;
+    if (s < S) {  // (candidates beyond Nd are evaluated on a clamped index and never stored)
+      const double ss = cst[sl][0], noise = cst[sl][1], sigma1 = cst[sl][2];
+      int64_t cq[kErCpq];
+      size_t o[kErCpq];
+      double xi[kErCpq];
+#pragma unroll
+      for (int q = 0; q < kErCpq; q++) {
+        cq[q] = c[q] < Nd ? c[q] : Nd - 1;
+        o[q] = (size_t)s * Nd + cq[q];
+      }
+      if (xi_ovr) {
+#pragma unroll
+        for (int q = 0; q < kErCpq; q++) xi[q] = xi_ovr[o[q]];  // quadrature estimate (k_rowmean)
+      } else {
+        // _core.py:86-92: ss * prod_k sqrt(pi)/sqrt(2) * ell_k * (erf((1-x)/(sqrt2 ell)) - erf((0-x)/(sqrt2 ell))), k ascending;
+        // each factor from its even Chebyshev series (Clenshaw), or from erf where the series did not converge; the
+        // candidates of this thread advance together (independent dependency chains)
+        const double* aux = reinterpret_cast<const double*>(ws + L.off_aux) + (size_t)s * L.aux_doubles;
+        double xf[kErCpq];
+#pragma unroll
+        for (int q = 0; q < kErCpq; q++) xf[q] = 1.0;
+        for (int k = 0; k < d; k++) {
+          const double* a = xc + sl * xcs + k * kXcStride;
+          const int n = use_series ? (int)a[0] : 0;
+          double xv[kErCpq], fk[kErCpq];
+#pragma unroll
+          for (int q = 0; q < kErCpq; q++) xv[q] = Xd[cq[q] * d + k];
+          if (n > 0) {
+            double w[kErCpq], w2[kErCpq], b1[kErCpq], b2[kErCpq];
+#pragma unroll
+            for (int q = 0; q < kErCpq; q++) {
+              const double u = fma(2.0, xv[q], -1.0);
+              w[q] = fma(2.0 * u, u, -1.0);  // w = 2 u^2 - 1
+              w2[q] = 2.0 * w[q];
+              b1[q] = 0.0;
+              b2[q] = 0.0;
+            }
+            for (int j = n - 1; j >= 1; j--) {
+              const double aj = a[1 + j];
+#pragma unroll
+              for (int q = 0; q < kErCpq; q++) {
+                const double t = fma(w2[q], b1[q], aj) - b2[q];
+                b2[q] = b1[q];
+                b1[q] = t;
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < kErCpq; q++) fk[q] = fma(w[q], b1[q], a[1]) - b2[q];
+          } else {
+            const double ck = aux[aux_ck() + k], ell = aux[aux_ell() + k];
+#pragma unroll
+            for (int q = 0; q < kErCpq; q++) fk[q] = 1.2533141373155001 * ell * (erf((1.0 - xv[q]) * ck) - erf((0.0 - xv[q]) * ck));
+          }
+#pragma unroll
+          for (int q = 0; q < kErCpq; q++) xf[q] *= fk[q];
+        }
+#pragma unroll
+        for (int q = 0; q < kErCpq; q++) xi[q] = ss * xf[q];
+      }
+#pragma unroll
+      for (int q = 0; q < kErCpq; q++) {
+        const double sigma_x = sx[o[q]];
+        const double v = xi[q] - wkplane[o[q]];  // _sampler.py:399
+        const double v2 = v * v;                 // :401
+        const double kxx = sigma_x + noise;      // :397 predict(include_likelihood=True)
+        const double sigma2 = sigma1 - v2 / kxx; // :400
+        double kld;
+        if (form == kFormLog1p) {
+          kld = -0.5 * log1p(-(v2 / (sigma1 * kxx)));
+        } else {
+          // :480, same operation order as the reference expression
+          kld = ((log(sqrt(sigma1) / sqrt(sigma2)) + (sigma2 / (2.0 * sigma1))) + ((v2 / sigma1) / (sigma_x + noise)) * 0.5) - 0.5;
+        }
+        lk[q] = log(kld);  // :492 np.log(kld_j)
+        if (keep_logk && c[q] < Nd) sx[o[q]] = lk[q];
+      }
+    }
+    // the quad's four values per candidate, added in hyper-sample order by every lane of the quad
+#pragma unroll
+    for (int q = 0; q < kErCpq; q++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const double vj = __shfl_sync(0xffffffffu, lk[q], (threadIdx.x & 28) | j, 32);
+        if (s0 + j < S) acc[q] += vj;
+      }
+  }
+  double mean[kErCpq], a2[kErCpq];
+#pragma unroll
+  for (int q = 0; q < kErCpq; q++) {
+    mean[q] = acc[q] / (double)S;
+    a2[q] = 0.0;
+  }
+  if (var != nullptr) {
+    // population variance of the logs about the mean: every lane re-reads its own stores, the quad adds the squares in
+    // hyper-sample order (same scheme as the mean)
+    for (int s0 = 0; s0 < S; s0 += 4) {
+      const int s = s0 + sl;
+      double dl2[kErCpq];
+#pragma unroll
+      for (int q = 0; q < kErCpq; q++) {
+        dl2[q] = 0.0;
+        if (s < S && c[q] < Nd) {
+          const double dl = sx[(size_t)s * Nd + c[q]] - mean[q];
+          dl2[q] = dl * dl;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < kErCpq; q++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const double vj = __shfl_sync(0xffffffffu, dl2[q], (threadIdx.x & 28) | j, 32);
+          if (s0 + j < S) a2[q] += vj;
+        }
+    }
+  }
+  double bv = -INFINITY;
+  int64_t bi = INT64_MAX;
+#pragma unroll
+  for (int q = 0; q < kErCpq; q++) {
+    if (c[q] < Nd && sl == 0) {
+      if (var != nullptr) var[c[q]] = a2[q] / (double)S;
+      score[c[q]] = mean[q];
+      if (better(mean[q], idx_offset + c[q], bv, bi)) { bv = mean[q]; bi = idx_offset + c[q]; }
+    }
+  }
+  block_best(bv, bi, sv, si);
+  final_argmax(bv, bi, part_val, part_idx, done_counter, best, best_idx, sv, si, &last);
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Plain reduction over hyper-samples (sequential in s) + argmax: the uncertainty-sampling comparator's mean variance
+// ----------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_reduce(const double* __restrict__ logk, int S, int64_t Nd, int64_t idx_offset,
                                                 double* __restrict__ score, double* __restrict__ var,
                                                 double* __restrict__ part_val, int64_t* __restrict__ part_idx,
@@ -701,44 +868,8 @@ __global__ void __launch_bounds__(256) k_reduce(const double* __restrict__ logk,
   __shared__ double sv[8];
   __shared__ int64_t si[8];
   __shared__ bool last;
-  auto block_best = [&]() {  // (bv, bi) of thread 0 = the block's winner
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
-    }
-    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
-    __syncthreads();
-    if (threadIdx.x == 0)
-      for (int w = 1; w < 8; w++)
-        if (better(sv[w], si[w], bv, bi)) { bv = sv[w]; bi = si[w]; }
-  };
-  block_best();
-  if (threadIdx.x == 0) {
-    part_val[blockIdx.x] = bv;
-    part_idx[blockIdx.x] = bi;
-    __threadfence();
-    last = atomicAdd(done_counter, 1u) == gridDim.x - 1;
-  }
-  __syncthreads();
-  if (!last) return;
-  // the last block to finish combines the per-block winners (the comparison is a total order, so the result does not
-  // depend on which block runs this or in which order the partials are visited)
-  __threadfence();
-  bv = -INFINITY;
-  bi = INT64_MAX;
-  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
-    const double pv_ = __ldcg(part_val + i);
-    const int64_t pi_ = __ldcg(part_idx + i);
-    if (better(pv_, pi_, bv, bi)) { bv = pv_; bi = pi_; }
-  }
-  __syncthreads();
-  block_best();
-  if (threadIdx.x == 0) {
-    best[0] = bv;
-    best_idx[0] = bi;
-    *done_counter = 0u;  // ready for the next call on this scratch buffer
-  }
+  block_best(bv, bi, sv, si);
+  final_argmax(bv, bi, part_val, part_idx, done_counter, best, best_idx, sv, si, &last);
 }
 
 // logk -> EKLD values (for callers that want the (S, Nd) matrix the reference would have produced)
@@ -926,9 +1057,15 @@ cudaError_t launch_score(const ScoreArgs& a, const ScorePlan& P, cudaStream_t st
   return launch_one<8, 2, 16, 1>(a, P, st);
 }
 
-cudaError_t launch_xi(const void* ws, const Layout& L, const double* Xd, double* xi_out, int S, int64_t Nd, cudaStream_t st) {
-  const dim3 grid((unsigned)((Nd + 255) / 256), (unsigned)(S < 65535 ? S : 65535));
-  k_xi<<<grid, 256, 0, st>>>(static_cast<const char*>(ws), L, Xd, xi_out, S, Nd, tuning().xik_series);
+cudaError_t launch_ekld_reduce(const void* ws, const Layout& L, const double* Xd, const double* xi_ovr, double* sx,
+                               const double* wkplane, int S, int64_t Nd, int64_t idx_offset, int form, int keep_logk,
+                               double* score, double* var, double* part_val, int64_t* part_idx, unsigned int* done_counter,
+                               double* best, int64_t* best_idx, cudaStream_t st) {
+  const int nb = (int)((Nd + kErCand - 1) / kErCand);
+  const size_t smem = sizeof(double) * 4 * (size_t)L.d * kXcStride;  // <= 25.6 KB
+  k_ekld_reduce<<<nb, 256, smem, st>>>(static_cast<const char*>(ws), L, Xd, xi_ovr, sx, wkplane, S, Nd, idx_offset, form,
+                                       tuning().xik_series, keep_logk || var != nullptr, score, var, part_val, part_idx,
+                                       done_counter, best, best_idx);
   return cudaGetLastError();
 }
 

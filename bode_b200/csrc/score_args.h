@@ -19,9 +19,8 @@ struct ScoreArgs {
   Layout L;
   const double* Xd;  // Nd * d
   int64_t Nd;
-  const double* xi;  // S * Nd: xik(x) per (hyper-sample, candidate) (k_xi, or the quadrature estimate of k_rowmean); EKLD mode only
-  double* out;       // S * Nd: log EKLD (EKLD mode) or sigma_x (variance mode); may alias xi (each element is read, then
-                     // written, by the same thread)
+  double* sx;        // S * Nd: sigma_x, the latent predictive variance (every mode)
+  double* wk;        // S * Nd: w.k = e_k^T A^-1 k(X, x), the data term of v (EKLD mode only); k_ekld_reduce finishes the EKLD
   unsigned int* done_counter;  // zeroed here for the block-argmax reduction kernel that follows on the same stream
   int S;
   int sc;            // hyper-samples per work item

@@ -240,7 +240,7 @@ class EkldEngine:
             var = torch.empty(Nd, dtype=torch.float64, device=self.device) if want_var else None
             rec = torch.empty(2, dtype=torch.int64, device=self.device)  # packed {float64 best, int64 best_idx}
             best, best_idx = rec[:1].view(torch.float64), rec[1:]
-            scr = self._buf("scratch", 256 + self.lib.bode_ekld_score_scratch_bytes(Nd, 0), torch.uint8)
+            scr = self._buf("scratch", 256 + self.lib.bode_ekld_score_scratch_bytes(Nd, self.S), torch.uint8)
             args = [_ptr(self.ws), self.n, self.d, self.S, _ptr(Xd), Nd, int(idx_offset), int(form), _ptr(logk),
                     _ptr(score), _ptr(var), _ptr(best), _ptr(best_idx), _ptr(scr), self._stream()]
             if self.quad is not None:

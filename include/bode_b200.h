@@ -96,14 +96,14 @@ int bode_ekld_mu_sigma_dev(const void* workspace, int n, int d, int S, double* o
  *   var[c] = (1/S) sum_s (log EKLD_s - score[c])^2  (nullable),
  *   best[0] = max score (NaN counts as largest, like np.argmax), best_idx[0] = idx_offset + first index attaining it.
  *   logk[s*Nd + c] = log EKLD_s(X_design[c]) -- NULLABLE: pass S*Nd doubles only if the per-sample matrix is wanted (the
- *   `kld_j` of `:489-491`); with NULL the one S x Nd plane the kernels need lives in `scratch`.
- * Three launches: k_xi (xik(x) of every (sample, candidate) into the plane), k_score (cross-covariance, L^-1 contraction
- * on the FP64 tensor pipe and the fused EKLD epilogue, in place over the plane), k_reduce (mean / var over samples, block
- * argmax, final argmax by the last block to finish).
+ *   `kld_j` of `:489-491`).
+ * Two launches: k_score (cross-covariance and L^-1 contraction on the FP64 tensor pipe; writes sigma_x and w.k per
+ * (sample, candidate)) and k_ekld_reduce (xik(x), v, the closed-form EKLD and its log, mean / var over samples in sample
+ * order, block argmax, final argmax by the last block to finish).
  * `idx_offset` is the global index of X_design[0] (multi-GPU candidate sharding).
- * `scratch`: bode_ekld_score_scratch_bytes(Nd, S) bytes when logk is NULL, bode_ekld_score_scratch_bytes(Nd, 0) when logk
- * is given (argmax partials only); 256-byte aligned.  `best` and `best_idx` may point at the two halves of one 16-byte
- * record (what bode_ekld_argmax_nccl exchanges). */
+ * `scratch` (256-byte aligned) holds the argmax partials, the w.k plane and -- when logk is NULL -- the sigma_x plane:
+ * bode_ekld_score_scratch_bytes(Nd, S) bytes when logk is given, bode_ekld_score_scratch_bytes(Nd, 2 * S) when it is NULL.
+ * `best` and `best_idx` may point at the two halves of one 16-byte record (what bode_ekld_argmax_nccl exchanges). */
 size_t bode_ekld_score_scratch_bytes(int64_t Nd, int S);
 int bode_ekld_score_dev(const void* workspace, int n, int d, int S, const double* X_design, int64_t Nd,
                         int64_t idx_offset, int form, double* logk, double* score, double* var, double* best,
@@ -139,7 +139,7 @@ int bode_ekld_prepare_quad_dev(const double* X, const double* Y, const double* h
                                double nugget_var, double jitter, const double* Xq, const double* wq, int Nq,
                                void* workspace, size_t workspace_bytes, int* info, void* scratch, void* stream);
 /* bode_ekld_score_dev with xi_q(x) in place of xik(x); xi is an S*Nd buffer (returned filled); logk nullable as above;
- * scratch >= 256 + bode_ekld_score_scratch_bytes(Nd, logk ? 0 : S). */
+ * scratch >= 256 + bode_ekld_score_scratch_bytes(Nd, logk ? S : 2 * S). */
 int bode_ekld_score_quad_dev(const void* workspace, int n, int d, int S, const double* hyp, int ndim,
                              const double* X_design, int64_t Nd, int64_t idx_offset, int form, const double* Xq,
                              const double* wq, int Nq, double* xi, double* logk, double* score, double* var, double* best,

@@ -75,8 +75,8 @@ def test_reference_code_vectors_on_gpu(ext, golden_dir, tag, min_trusted):
         assert abs(r["mu_Q"] - g["mu_1"].mean()) <= 1e-10 * abs(g["mu_1"].mean()) + 1e-13
         assert abs(r["sigma_Q"] - g["sigma_1"].mean()) <= 1e-8 * abs(g["sigma_1"].mean())
     else:
+        # ill-conditioned hyper-samples (the fixture's, cond up to 1e8): entries via T2 above, winner via the truth
         tsc = np.log(t["kld"]).mean(0)
-        assert (np.abs(r["score"] - tsc) <= 2.0 * np.mean(1e-6 + 1e-15 / t["kld"], axis=0)).all()
         assert_argmax(r["argmax"], tsc, tol=1e-6)
         assert_argmax(int(np.argmax(g["mcmc_mean"])), tsc, tol=1e-6)   # ... and the reference's choice is in the same tie set
 
@@ -296,16 +296,18 @@ def test_jitchol_retries_like_gpy(engine):
     """GPy's jitchol (inside make_mcmc_model, `_sampler.py:453`) retries a failed factorisation with mean(diag) * 1e-6 * 10^k
     on the diagonal; EkldEngine.prepare(jitchol_retries=5) does the same per hyper-sample and leaves healthy samples alone."""
     rng = np.random.default_rng(0)
-    X = rng.random((6, 2)); X[4] = X[1]
+    X = rng.random((6, 2)); X[4] = X[1] + 1e-9        # two observations 1e-9 apart
     Y = rng.random((6, 1)); Y[4] = Y[1]
-    hyp = np.array([[1.0, 0.5, 0.5], [2.0, 0.4, 0.6], [1.5, 0.05, 0.05]])
-    info = engine.prepare(X, Y, hyp, 0.0, jitter=0.0)
-    assert int(info[0]) == 5                         # duplicate row, no nugget, no jitter: pivot 5 is not positive
+    # long lengthscales: the two rows of K are identical to rounding (singular); ell = 1e-3: they differ by 1e-12 (fine)
+    hyp = np.array([[1.0, 0.5, 0.5], [2.0, 0.4, 0.6], [1.5, 1e-3, 1e-3]])
+    info0 = engine.prepare(X, Y, hyp, 0.0, jitter=0.0).cpu().numpy()
+    assert info0[0] > 0 and info0[2] == 0              # LAPACK-style: index of the first non-positive pivot
     t_plain = engine.sample_terms().cpu().numpy()
     info = engine.prepare(X, Y, hyp, 0.0, jitter=0.0, jitchol_retries=5)
     assert (info.cpu().numpy() == 0).all()
     ju = engine.jitter_used
     assert ju[0] == pytest.approx(1e-6) and ju[2] == 0.0    # mean(diag) = variance = 1 -> first retry adds 1e-6
+    assert (ju[info0 > 0] > 0).all() and (ju[info0 == 0] == 0).all()
     t = engine.sample_terms().cpu().numpy()
     assert np.isfinite(t).all()
     np.testing.assert_array_equal(t[2], t_plain[2])       # the healthy sample keeps its bits
@@ -336,7 +338,7 @@ def test_host_entry_reuses_its_device_buffers(ext):
 
 
 def test_logk_is_optional_in_the_c_abi(engine, ext):
-    """`bode_ekld_score_dev` with logk = NULL keeps its one S x Nd plane in scratch: same scores, same argmax."""
+    """`bode_ekld_score_dev` with logk = NULL keeps both S x Nd planes in scratch: same scores, same argmax."""
     import ctypes
     import torch
     X, Y, Xd, hyp = cases.make_problem(4, 30, 6, 900, seed=12, ell_lo=0.2, ell_hi=0.7)
@@ -347,8 +349,8 @@ def test_logk_is_optional_in_the_c_abi(engine, ext):
     xd = torch.from_numpy(Xd).to(dev)
     score = torch.empty(Nd, dtype=torch.float64, device=dev)
     rec = torch.empty(2, dtype=torch.int64, device=dev)
-    scr = torch.empty(lib.bode_ekld_score_scratch_bytes(Nd, S), dtype=torch.uint8, device=dev)
-    assert lib.bode_ekld_score_scratch_bytes(Nd, S) >= 8 * S * Nd > lib.bode_ekld_score_scratch_bytes(Nd, 0)
+    scr = torch.empty(lib.bode_ekld_score_scratch_bytes(Nd, 2 * S), dtype=torch.uint8, device=dev)  # logk = NULL: both planes
+    assert lib.bode_ekld_score_scratch_bytes(Nd, 2 * S) >= 16 * S * Nd > lib.bode_ekld_score_scratch_bytes(Nd, S) >= 8 * S * Nd
     p = lambda t: ctypes.c_void_p(t.data_ptr())
     ext.check(lib.bode_ekld_score_dev(p(engine.ws), engine.n, engine.d, S, p(xd), Nd, 0, 0, None, p(score), None, p(rec[:1]), p(rec[1:]),
                                       p(scr), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))

@@ -7,6 +7,14 @@ T1 (element-wise, well-conditioned inputs):  |gpu - oracle| <= 1e-9 * |oracle| +
     (`_sampler.py:480`: log(..) + s2/(2 s1) + v^2/(2 s1 kxx) - 1/2, terms of size 0.5 that sum to ~EKLD), which
     carries ~2e-16 absolute rounding noise in *both* the oracle and the CUDA path.
 
+    For entries far below the sample's largest EKLD the bar is relative to the geometric mean of the entry and that
+    maximum:  |gpu - oracle| <= 1e-9 * sqrt(|oracle| * max_c |oracle|) + 1e-15  where |oracle| < 1e-3 * max_c |oracle|.
+    Reason: EKLD ~ v^2 / (2 sigma_1 k_xx) near the zeros of v = xik(x) - e^T A^-1 k(X, x), and v carries an ABSOLUTE
+    rounding error that is the same for every candidate, so d EKLD ~ |v| dv ~ sqrt(EKLD).  A sample that meets 1e-9 at
+    its maximum therefore meets 1e-9 * sqrt(EKLD * max) elsewhere -- and cannot do better: the reference's own code,
+    run per candidate, misses the long-double truth by 2.7e-6 relative at an EKLD of 2e-11 next to a zero of v on a
+    hyper-sample whose large entries are accurate to 1e-10 (tests/golden/ekld_ref_c1.npz, sample 37).
+
 T2 (ill-conditioned hyper-samples):  the reference route (explicit inverse via dpotri) is itself only accurate to
     ~eps*cond(A) (SURVEY.md note C; up to 1e-2 relative at cond 1e7), so oracle and CUDA path are each compared with
     an 80-bit long-double evaluation (oracle/ekld_truth.c) and the CUDA path must be at least as accurate as the
@@ -28,8 +36,10 @@ ATOL_FORMULA = 1e-15
 
 
 def assert_t1(got, ref, what="EKLD"):
-    got = np.asarray(got); ref = np.asarray(ref)
-    bad = ~(np.abs(got - ref) <= RTOL * np.abs(ref) + ATOL_FORMULA)
+    got = np.atleast_2d(np.asarray(got)); ref = np.atleast_2d(np.asarray(ref))
+    rowmax = np.nanmax(np.abs(ref), axis=1, keepdims=True)
+    scale = np.where(np.abs(ref) >= 1e-3 * rowmax, np.abs(ref), np.sqrt(np.abs(ref) * rowmax))
+    bad = ~(np.abs(got - ref) <= RTOL * scale + ATOL_FORMULA)
     assert not bad.any(), "%s: %d entries outside 1e-9 rel + 1e-15 abs; worst rel %.3e" % (
         what, int(bad.sum()), float(np.nanmax(np.abs(got - ref) / np.abs(ref))))
 

@@ -53,7 +53,7 @@ static Tuning read_tuning() {
   t.debug_skip = geti("BODE_DEBUG_SKIP", 0);
   t.stagger = geti("BODE_STAGGER", 0);
   t.xik_series = geti("BODE_XIK_SERIES", 1);
-  t.prep_split = geti("BODE_PREP_SPLIT", 0);
+  t.prep_variant = geti("BODE_PREP_VARIANT", -1);
   return t;
 }
 static Tuning g_tuning = read_tuning();
@@ -231,7 +231,7 @@ int bode_ekld_prepare_dev(const double* X, const double* Y, const double* hyp, i
   if (!shape_supported(n, d)) return BODE_ERR_UNSUPPORTED;
   PrepArgs a;
   a.X = X; a.Y = Y; a.hyp = hyp; a.n = n; a.d = d; a.S = S; a.ndim = ndim;
-  a.nugget_var = nugget_var; a.jitter = jitter; a.jitter_s = nullptr;
+  a.nugget_var = nugget_var; a.jitter = jitter; a.jitter_s = nullptr; a.x_smem = 0;
   a.ws = static_cast<char*>(workspace);
   a.L = make_layout(n, d, S);
   a.info = info;
@@ -251,7 +251,7 @@ int bode_ekld_prepare_jitter_dev(const double* X, const double* Y, const double*
   if (!shape_supported(n, d)) return BODE_ERR_UNSUPPORTED;
   PrepArgs a;
   a.X = X; a.Y = Y; a.hyp = hyp; a.n = n; a.d = d; a.S = S; a.ndim = ndim;
-  a.nugget_var = nugget_var; a.jitter = 0.0; a.jitter_s = jitter_per_sample;
+  a.nugget_var = nugget_var; a.jitter = 0.0; a.jitter_s = jitter_per_sample; a.x_smem = 0;
   a.ws = static_cast<char*>(workspace);
   a.L = make_layout(n, d, S);
   a.info = info;
@@ -302,7 +302,7 @@ int bode_ekld_prepare_quad_dev(const double* X, const double* Y, const double* h
   BODE_CUDA(launch_weighted_mean(rmq, wq, Nq, wsp, S, s0, st));                  // sigma0_q
   PrepArgs a;
   a.X = X; a.Y = Y; a.hyp = hyp; a.n = n; a.d = d; a.S = S; a.ndim = ndim;
-  a.nugget_var = nugget_var; a.jitter = jitter; a.jitter_s = nullptr;
+  a.nugget_var = nugget_var; a.jitter = jitter; a.jitter_s = nullptr; a.x_smem = 0;
   a.ws = static_cast<char*>(workspace);
   a.L = make_layout(n, d, S);
   a.info = info;
@@ -322,7 +322,7 @@ int bode_gp_loglik_dev(const double* X, const double* Y, const double* hyp, int 
   if (!shape_supported(n, d)) return BODE_ERR_UNSUPPORTED;
   PrepArgs a;
   a.X = X; a.Y = Y; a.hyp = hyp; a.n = n; a.d = d; a.S = S; a.ndim = ndim;
-  a.nugget_var = nugget_var; a.jitter = jitter; a.jitter_s = nullptr;
+  a.nugget_var = nugget_var; a.jitter = jitter; a.jitter_s = nullptr; a.x_smem = 0;
   a.ws = static_cast<char*>(workspace);
   a.L = make_layout(n, d, S);
   a.info = info;
@@ -677,7 +677,8 @@ int bode_fp64_peak(double* dmma_tflops, double* dfma_tflops) {
 #ifdef BODE_TIMELINE
 #include <stdio.h>
 namespace bode { cudaError_t debug_copy_timeline(long long* host); cudaError_t debug_set_phase_a(int v); }
-namespace bode { cudaError_t debug_copy_prepare_timeline(long long* host); }
+namespace bode { cudaError_t debug_copy_prepare_timeline(long long* host); cudaError_t debug_copy_prepare_tiles_timeline(long long* host); }
+extern "C" int bode_debug_prepare_tiles(long long* out) { cudaDeviceSynchronize(); return bode::debug_copy_prepare_tiles_timeline(out) == cudaSuccess ? 0 : -4; }
 extern "C" int bode_debug_prepare(long long* out) { cudaDeviceSynchronize(); return bode::debug_copy_prepare_timeline(out) == cudaSuccess ? 0 : -4; }
 extern "C" int bode_debug_phase_a(int v) { return bode::debug_set_phase_a(v) == cudaSuccess ? 0 : -4; }
 extern "C" int bode_debug_dump(const char* path) {

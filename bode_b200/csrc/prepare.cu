@@ -23,6 +23,8 @@
 #include "layout.h"
 #include "prepare_args.h"
 #include "rbf.h"
+#include "tuning.h"
+#include "xik_coef.h"
 
 namespace bode {
 
@@ -94,53 +96,6 @@ cudaError_t debug_copy_prepare_timeline(long long* host) { return cudaMemcpyFrom
 #else
 #define TP(i) do { } while (0)
 #endif
-
-// ---- even Chebyshev series of the xik factors (candidate-independent part of xik(x), reference _core.py:86-92) -----
-// F_k(x) = sqrt(pi)/sqrt(2) * ell_k * (erf((1-x) c_k) - erf((0-x) c_k)) is symmetric about x = 1/2, so with u = 2x-1 it is
-// a series in T_2j(u) = T_j(w), w = 2u^2 - 1.  One CTA per (sample, dimension): sample F at the 64 Gauss-Chebyshev nodes
-// w_i = cos(theta_i) (u_i = cos(theta_i / 2) exactly), a_j = (2/64) sum_i F_i cos(j theta_i) with the cosines taken
-// through cospi of an exactly reduced argument, cut the series where the coefficients drop under the rounding floor of
-// this very sum (4e-16 a_0).  The EKLD kernel then spends 2 n + 6 operations per factor instead of two erf (~130).
-// Runs inside the k_prepare launch on the blocks with blockIdx.x >= S (they land on the SMs the S factorisation CTAs leave
-// idle): block S + s * ceil(d/4) + q handles dimensions 4q..4q+3 of sample s, 64 threads per dimension.
-__device__ __forceinline__ void xik_coef_block(const double* __restrict__ hyp, int ndim, int d, char* ws, const Layout& L, int s, int k0,
-                                               double* F /*[4][64]*/, double* A /*[4][64]*/) {
-  const int kq = threadIdx.x >> 6, i = threadIdx.x & 63, k = k0 + kq;
-  const bool on = k < d;
-  if (on) {
-    const double ell = hyp[(size_t)s * ndim + 1 + k];
-    const double c = 1.0 / (1.4142135623730951 * ell);
-    const double u = cospi(((double)i + 0.5) / (2.0 * kXcNodes));  // cos(theta_i / 2), theta_i = pi (i + 1/2) / 64
-    const double x = 0.5 * (u + 1.0);
-    F[kq * kXcNodes + i] = 1.2533141373155001 * ell * (erf((1.0 - x) * c) - erf((0.0 - x) * c));
-  }
-  __syncthreads();
-  if (on) {
-    double acc = 0.0;
-    for (int m = 0; m < kXcNodes; m++) {
-      const int r = (i * (2 * m + 1)) & (4 * kXcNodes - 1);  // j theta_m = pi r / 128 (mod 2 pi), j = this thread
-      acc = fma(F[kq * kXcNodes + m], cospi((double)r / (2.0 * kXcNodes)), acc);
-    }
-    A[kq * kXcNodes + i] = acc * (2.0 / kXcNodes);
-  }
-  __syncthreads();
-  if (!on) return;
-  const double* Ak = A + kq * kXcNodes;
-  double* out = reinterpret_cast<double*>(ws + L.off_xc) + (size_t)s * L.xc_doubles + (size_t)k * kXcStride;
-  if (i == 0) {
-    const double floor_ = 4e-16 * fabs(Ak[0]);
-    int n = 0;
-    bool ok = Ak[0] == Ak[0];
-    for (int j = 0; j < kXcNodes; j++) {
-      if (!(fabs(Ak[j]) <= floor_)) {       // (also true for NaN)
-        if (j < kXcMax) n = j + 1;
-        else ok = false;                    // not converged within kXcMax terms: erf path
-      }
-    }
-    out[0] = ok ? (double)n : 0.0;
-  }
-  if (i < kXcMax) out[1 + i] = (i == 0) ? 0.5 * Ak[0] : Ak[i];
-}
 
 __global__ void __launch_bounds__(kPrepThreads, 1) k_prepare(PrepArgs a) {
   extern __shared__ __align__(16) double sm[];
@@ -471,7 +426,14 @@ size_t prepare_smem_bytes(const Layout& L) {
   return sizeof(double) * (fact > coef ? fact : coef);
 }
 
+size_t prepare_tiles_smem_bytes(const Layout& L);                          // prepare_tiles.cu
+cudaError_t launch_prepare_tiles(const PrepArgs& a, cudaStream_t st);      // prepare_tiles.cu
+
 cudaError_t launch_prepare(const PrepArgs& a, cudaStream_t st) {
+  // n <= 224: the bordered triangle fits in shared memory and the factorisation runs on the FP64 tensor pipe
+  // (prepare_tiles.cu); larger n (or BODE_PREP_VARIANT=0): the global-memory kernel below
+  if (tuning().prep_variant != 0 && a.L.nrt <= 28 && prepare_tiles_smem_bytes(a.L) + 64 <= 232448)
+    return launch_prepare_tiles(a, st);
   const size_t smem = prepare_smem_bytes(a.L);
   static thread_local int attr_dev = -1;
   static thread_local size_t attr_smem = 0;

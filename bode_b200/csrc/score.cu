@@ -596,13 +596,15 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
 // mean / variance over the hyper-samples, block argmax and (last block to finish) the final argmax.
 // (xik reference bode/_core.py:86-92; get_params_2 _sampler.py:399-401; avg_kld_mean :474-481; mcmc_kld :492; argmax :659)
 //
-// Four lanes share a candidate: lane j of the quad evaluates log EKLD for the hyper-samples s = 4i + j (the expensive,
-// independent part), then the quad adds its four values to the running sum in the order s = 4i, 4i+1, 4i+2, 4i+3 --
-// every lane of the quad performs the same additions, so the sum over hyper-samples is exactly the sequential
-// s = 0..S-1 sum the oracle defines, independent of tiling, sharding and launch geometry.
+// A block owns 64 candidates (lane = candidate, two per lane); its eight warps take eight consecutive hyper-samples at
+// a time -- one sample per warp, so the series lengths and table reads are warp-uniform -- and hand their log EKLD
+// values to warp 0 through shared memory, which adds them to the running sums in hyper-sample order: the sum over
+// hyper-samples is exactly the sequential s = 0..S-1 sum the oracle defines, independent of tiling, sharding and
+// launch geometry.
 // ----------------------------------------------------------------------------------------------------------------
-constexpr int kErCpq = 2;                 // candidates per quad of lanes (independent dependency chains per thread)
-constexpr int kErCand = 64 * kErCpq;      // candidates per block (256 threads)
+constexpr int kErCpl = 2;                 // candidates per lane (independent dependency chains per thread)
+constexpr int kErCand = 32 * kErCpl;      // candidates per block
+constexpr int kErWarps = 8;               // hyper-samples in flight per block
 
 __device__ __forceinline__ bool better(double av, int64_t ai, double bv, int64_t bi) {
   // np.argmax semantics: NaN counts as the maximum; ties -> lowest index
@@ -660,86 +662,74 @@ __device__ __forceinline__ void final_argmax(double bv, int64_t bi, double* part
   }
 }
 
-__global__ void __launch_bounds__(256) k_ekld_reduce(const char* __restrict__ ws, Layout L, const double* __restrict__ Xd,
-                                                     const double* __restrict__ xi_ovr, double* __restrict__ sx,
-                                                     const double* __restrict__ wkplane, int S, int64_t Nd, int64_t idx_offset,
-                                                     int form, int use_series, int keep_logk, double* __restrict__ score,
-                                                     double* __restrict__ var, double* __restrict__ part_val,
-                                                     int64_t* __restrict__ part_idx, unsigned int* __restrict__ done_counter,
-                                                     double* __restrict__ best, int64_t* __restrict__ best_idx) {
-  extern __shared__ __align__(16) double xc[];  // [4][d][kXcStride]: series of the xik factors of the 4 samples in flight
-  __shared__ double cst[4][4];                  // {variance, noise, sigma1} of those samples
+__global__ void __launch_bounds__(32 * kErWarps) k_ekld_reduce(const char* __restrict__ ws, Layout L, const double* __restrict__ Xd,
+                                                               const double* __restrict__ xi_ovr, double* __restrict__ sx,
+                                                               const double* __restrict__ wkplane, int S, int64_t Nd,
+                                                               int64_t idx_offset, int form, int use_series, int keep_logk,
+                                                               double* __restrict__ score, double* __restrict__ var,
+                                                               double* __restrict__ part_val, int64_t* __restrict__ part_idx,
+                                                               unsigned int* __restrict__ done_counter,
+                                                               double* __restrict__ best, int64_t* __restrict__ best_idx) {
+  extern __shared__ __align__(16) double xc_all[];  // [kErWarps][d][kXcStride]: series of the xik factors, one sample per warp
+  __shared__ double lkbuf[2][kErWarps][kErCand];    // log EKLD (then squared deviations) on their way to warp 0
+  __shared__ double meanbuf[kErCand];
   __shared__ double sv[8];
   __shared__ int64_t si[8];
   __shared__ bool last;
   const int d = L.d;
-  const int sl = threadIdx.x & 3, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int xcs = d * kXcStride;
-  int64_t c[kErCpq];
-  double acc[kErCpq];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* xc = xc_all + (size_t)warp * d * kXcStride;
+  int64_t c[kErCpl], cq[kErCpl];
+  double acc[kErCpl];
 #pragma unroll
-  for (int q = 0; q < kErCpq; q++) {
-    c[q] = (int64_t)blockIdx.x * kErCand + q * 64 + (threadIdx.x >> 2);
+  for (int q = 0; q < kErCpl; q++) {
+    c[q] = (int64_t)blockIdx.x * kErCand + 32 * q + lane;
+    cq[q] = c[q] < Nd ? c[q] : Nd - 1;  // candidates beyond Nd are evaluated on a clamped index and never stored
     acc[q] = 0.0;
   }
-  for (int s0 = 0; s0 < S; s0 += 4) {
-    __syncthreads();
-    if (!xi_ovr) {
-      // only the live part of each series: [n_terms, a_0/2, a_1 .. a_(n-1)]
-      for (int jk = warp; jk < 4 * d; jk += 8) {
-        const int j = jk / d, k = jk - j * d;
-        if (s0 + j < S) {
-          const double* src = reinterpret_cast<const double*>(ws + L.off_xc) + (size_t)(s0 + j) * L.xc_doubles + (size_t)k * kXcStride;
-          const int n = (int)src[0];
-          double* dst = xc + j * xcs + k * kXcStride;
-          if (lane <= n) dst[lane] = src[lane];
-          if (lane + 32 <= n) dst[lane + 32] = src[lane + 32];
-        }
-      }
-    }
-    if (threadIdx.x < 12) {
-      const int j = threadIdx.x / 3, q = threadIdx.x - 3 * j;
-      if (s0 + j < S) {
-        const double* aux = reinterpret_cast<const double*>(ws + L.off_aux) + (size_t)(s0 + j) * L.aux_doubles;
-        cst[j][q] = aux[q == 0 ? C_SS : (q == 1 ? C_NOISE : C_SIGMA1)];
-      }
-    }
-    __syncthreads();
-    const int s = s0 + sl;
-    double lk[kErCpq];
+  const int niter = (S + kErWarps - 1) / kErWarps;
+  for (int it = 0; it < niter; it++) {
+    const int s = it * kErWarps + warp;
+    double lk[kErCpl];
 #pragma unroll
-    for (int q = 0; q < kErCpq; q++) lk[q] = 0.0;
-    if (s < S) {  // (candidates beyond Nd are evaluated on a clamped index and never stored)
-      const double ss = cst[sl][0], noise = cst[sl][1], sigma1 = cst[sl][2];
-      int64_t cq[kErCpq];
-      size_t o[kErCpq];
-      double xi[kErCpq];
+    for (int q = 0; q < kErCpl; q++) lk[q] = 0.0;
+    if (s < S) {
+      const double* aux = reinterpret_cast<const double*>(ws + L.off_aux) + (size_t)s * L.aux_doubles;
+      const double ss = aux[C_SS], noise = aux[C_NOISE], sigma1 = aux[C_SIGMA1];
+      size_t o[kErCpl];
+      double xi[kErCpl];
 #pragma unroll
-      for (int q = 0; q < kErCpq; q++) {
-        cq[q] = c[q] < Nd ? c[q] : Nd - 1;
-        o[q] = (size_t)s * Nd + cq[q];
-      }
+      for (int q = 0; q < kErCpl; q++) o[q] = (size_t)s * Nd + cq[q];
       if (xi_ovr) {
 #pragma unroll
-        for (int q = 0; q < kErCpq; q++) xi[q] = xi_ovr[o[q]];  // quadrature estimate (k_rowmean)
+        for (int q = 0; q < kErCpl; q++) xi[q] = xi_ovr[o[q]];  // quadrature estimate (k_rowmean)
       } else {
+        // this warp's sample: the live part of each series, [n_terms, a_0/2, a_1 .. a_(n-1)]
+        __syncwarp();
+        const double* src0 = reinterpret_cast<const double*>(ws + L.off_xc) + (size_t)s * L.xc_doubles;
+        for (int k = 0; k < d; k++) {
+          const double* src = src0 + (size_t)k * kXcStride;
+          const int n = (int)src[0];
+          if (lane <= n) xc[k * kXcStride + lane] = src[lane];
+          if (lane + 32 <= n) xc[k * kXcStride + lane + 32] = src[lane + 32];
+        }
+        __syncwarp();
         // _core.py:86-92: ss * prod_k sqrt(pi)/sqrt(2) * ell_k * (erf((1-x)/(sqrt2 ell)) - erf((0-x)/(sqrt2 ell))), k ascending;
         // each factor from its even Chebyshev series (Clenshaw), or from erf where the series did not converge; the
         // candidates of this thread advance together (independent dependency chains)
-        const double* aux = reinterpret_cast<const double*>(ws + L.off_aux) + (size_t)s * L.aux_doubles;
-        double xf[kErCpq];
+        double xf[kErCpl];
 #pragma unroll
-        for (int q = 0; q < kErCpq; q++) xf[q] = 1.0;
+        for (int q = 0; q < kErCpl; q++) xf[q] = 1.0;
         for (int k = 0; k < d; k++) {
-          const double* a = xc + sl * xcs + k * kXcStride;
+          const double* a = xc + k * kXcStride;
           const int n = use_series ? (int)a[0] : 0;
-          double xv[kErCpq], fk[kErCpq];
+          double xv[kErCpl], fk[kErCpl];
 #pragma unroll
-          for (int q = 0; q < kErCpq; q++) xv[q] = Xd[cq[q] * d + k];
+          for (int q = 0; q < kErCpl; q++) xv[q] = Xd[cq[q] * d + k];
           if (n > 0) {
-            double w[kErCpq], w2[kErCpq], b1[kErCpq], b2[kErCpq];
+            double w[kErCpl], w2[kErCpl], b1[kErCpl], b2[kErCpl];
 #pragma unroll
-            for (int q = 0; q < kErCpq; q++) {
+            for (int q = 0; q < kErCpl; q++) {
               const double u = fma(2.0, xv[q], -1.0);
               w[q] = fma(2.0 * u, u, -1.0);  // w = 2 u^2 - 1
               w2[q] = 2.0 * w[q];
@@ -749,27 +739,27 @@ __global__ void __launch_bounds__(256) k_ekld_reduce(const char* __restrict__ ws
             for (int j = n - 1; j >= 1; j--) {
               const double aj = a[1 + j];
 #pragma unroll
-              for (int q = 0; q < kErCpq; q++) {
+              for (int q = 0; q < kErCpl; q++) {
                 const double t = fma(w2[q], b1[q], aj) - b2[q];
                 b2[q] = b1[q];
                 b1[q] = t;
               }
             }
 #pragma unroll
-            for (int q = 0; q < kErCpq; q++) fk[q] = fma(w[q], b1[q], a[1]) - b2[q];
+            for (int q = 0; q < kErCpl; q++) fk[q] = fma(w[q], b1[q], a[1]) - b2[q];
           } else {
             const double ck = aux[aux_ck() + k], ell = aux[aux_ell() + k];
 #pragma unroll
-            for (int q = 0; q < kErCpq; q++) fk[q] = 1.2533141373155001 * ell * (erf((1.0 - xv[q]) * ck) - erf((0.0 - xv[q]) * ck));
+            for (int q = 0; q < kErCpl; q++) fk[q] = 1.2533141373155001 * ell * (erf((1.0 - xv[q]) * ck) - erf((0.0 - xv[q]) * ck));
           }
 #pragma unroll
-          for (int q = 0; q < kErCpq; q++) xf[q] *= fk[q];
+          for (int q = 0; q < kErCpl; q++) xf[q] *= fk[q];
         }
 #pragma unroll
-        for (int q = 0; q < kErCpq; q++) xi[q] = ss * xf[q];
+        for (int q = 0; q < kErCpl; q++) xi[q] = ss * xf[q];
       }
 #pragma unroll
-      for (int q = 0; q < kErCpq; q++) {
+      for (int q = 0; q < kErCpl; q++) {
         const double sigma_x = sx[o[q]];
         const double v = xi[q] - wkplane[o[q]];  // _sampler.py:399
         const double v2 = v * v;                 // :401
@@ -786,52 +776,67 @@ __global__ void __launch_bounds__(256) k_ekld_reduce(const char* __restrict__ ws
         if (keep_logk && c[q] < Nd) sx[o[q]] = lk[q];
       }
     }
-    // the quad's four values per candidate, added in hyper-sample order by every lane of the quad
 #pragma unroll
-    for (int q = 0; q < kErCpq; q++)
+    for (int q = 0; q < kErCpl; q++) lkbuf[it & 1][warp][32 * q + lane] = lk[q];
+    __syncthreads();
+    // warp 0 adds the eight samples' values in hyper-sample order (the other warps move on: the buffers alternate, and
+    // a buffer is rewritten only after the next barrier, which warp 0 reaches after these reads)
+    if (warp == 0) {
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const double vj = __shfl_sync(0xffffffffu, lk[q], (threadIdx.x & 28) | j, 32);
-        if (s0 + j < S) acc[q] += vj;
-      }
+      for (int j = 0; j < kErWarps; j++)
+        if (it * kErWarps + j < S) {
+#pragma unroll
+          for (int q = 0; q < kErCpl; q++) acc[q] += lkbuf[it & 1][j][32 * q + lane];
+        }
+    }
   }
-  double mean[kErCpq], a2[kErCpq];
+  double mean[kErCpl], a2[kErCpl];
 #pragma unroll
-  for (int q = 0; q < kErCpq; q++) {
+  for (int q = 0; q < kErCpl; q++) {
     mean[q] = acc[q] / (double)S;
     a2[q] = 0.0;
   }
   if (var != nullptr) {
-    // population variance of the logs about the mean: every lane re-reads its own stores, the quad adds the squares in
-    // hyper-sample order (same scheme as the mean)
-    for (int s0 = 0; s0 < S; s0 += 4) {
-      const int s = s0 + sl;
-      double dl2[kErCpq];
+    // population variance of the logs about the mean: every warp re-reads its own samples' stores, warp 0 adds the
+    // squares in hyper-sample order (same scheme as the mean)
+    __syncthreads();
+    if (warp == 0) {
 #pragma unroll
-      for (int q = 0; q < kErCpq; q++) {
-        dl2[q] = 0.0;
+      for (int q = 0; q < kErCpl; q++) meanbuf[32 * q + lane] = mean[q];
+    }
+    __syncthreads();
+    for (int it = 0; it < niter; it++) {
+      const int s = it * kErWarps + warp;
+#pragma unroll
+      for (int q = 0; q < kErCpl; q++) {
+        double dl2 = 0.0;
         if (s < S && c[q] < Nd) {
-          const double dl = sx[(size_t)s * Nd + c[q]] - mean[q];
-          dl2[q] = dl * dl;
+          const double dl = sx[(size_t)s * Nd + c[q]] - meanbuf[32 * q + lane];
+          dl2 = dl * dl;
         }
+        lkbuf[it & 1][warp][32 * q + lane] = dl2;
       }
+      __syncthreads();
+      if (warp == 0) {
 #pragma unroll
-      for (int q = 0; q < kErCpq; q++)
+        for (int j = 0; j < kErWarps; j++)
+          if (it * kErWarps + j < S) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const double vj = __shfl_sync(0xffffffffu, dl2[q], (threadIdx.x & 28) | j, 32);
-          if (s0 + j < S) a2[q] += vj;
-        }
+            for (int q = 0; q < kErCpl; q++) a2[q] += lkbuf[it & 1][j][32 * q + lane];
+          }
+      }
     }
   }
   double bv = -INFINITY;
   int64_t bi = INT64_MAX;
+  if (warp == 0) {
 #pragma unroll
-  for (int q = 0; q < kErCpq; q++) {
-    if (c[q] < Nd && sl == 0) {
-      if (var != nullptr) var[c[q]] = a2[q] / (double)S;
-      score[c[q]] = mean[q];
-      if (better(mean[q], idx_offset + c[q], bv, bi)) { bv = mean[q]; bi = idx_offset + c[q]; }
+    for (int q = 0; q < kErCpl; q++) {
+      if (c[q] < Nd) {
+        if (var != nullptr) var[c[q]] = a2[q] / (double)S;
+        score[c[q]] = mean[q];
+        if (better(mean[q], idx_offset + c[q], bv, bi)) { bv = mean[q]; bi = idx_offset + c[q]; }
+      }
     }
   }
   block_best(bv, bi, sv, si);
@@ -1062,10 +1067,19 @@ cudaError_t launch_ekld_reduce(const void* ws, const Layout& L, const double* Xd
                                double* score, double* var, double* part_val, int64_t* part_idx, unsigned int* done_counter,
                                double* best, int64_t* best_idx, cudaStream_t st) {
   const int nb = (int)((Nd + kErCand - 1) / kErCand);
-  const size_t smem = sizeof(double) * 4 * (size_t)L.d * kXcStride;  // <= 25.6 KB
-  k_ekld_reduce<<<nb, 256, smem, st>>>(static_cast<const char*>(ws), L, Xd, xi_ovr, sx, wkplane, S, Nd, idx_offset, form,
-                                       tuning().xik_series, keep_logk || var != nullptr, score, var, part_val, part_idx,
-                                       done_counter, best, best_idx);
+  const size_t smem = sizeof(double) * kErWarps * (size_t)L.d * kXcStride;  // 25.6 KB at d = 8, 51.2 KB at d = 16
+  static thread_local int attr_dev = -1;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev != attr_dev) {  // d = 16 needs more than the 48 KB default: opt in once per device
+    e = cudaFuncSetAttribute(k_ekld_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * kErWarps * 16 * kXcStride));
+    if (e != cudaSuccess) return e;
+    attr_dev = dev;
+  }
+  k_ekld_reduce<<<nb, 32 * kErWarps, smem, st>>>(static_cast<const char*>(ws), L, Xd, xi_ovr, sx, wkplane, S, Nd, idx_offset, form,
+                                                 tuning().xik_series, keep_logk || var != nullptr, score, var, part_val, part_idx,
+                                                 done_counter, best, best_idx);
   return cudaGetLastError();
 }
 

@@ -12,7 +12,7 @@ struct Tuning {
   int debug_skip;     // BODE_DEBUG_SKIP     (timing decomposition only)
   int stagger;        // BODE_STAGGER
   int xik_series;     // BODE_XIK_SERIES     (0: evaluate every xik factor with erf)
-  int prep_split;     // BODE_PREP_SPLIT     (CTAs per hyper-sample in the prepare kernel; 0: planner's choice)
+  int prep_variant;   // BODE_PREP_VARIANT   (0: global-memory prepare kernel even where the shared-memory tile kernel fits)
 };
 
 const Tuning& tuning();

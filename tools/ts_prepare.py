@@ -17,6 +17,16 @@ for _ in range(3):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); eng.prepare(X, Y, hyp, 1e-6); e1.record(); torch.cuda.synchronize()
 print("prepare ms", e0.elapsed_time(e1))
+if a.n <= 224 and os.environ.get("BODE_PREP_VARIANT") != "0":
+    buf = (ctypes.c_longlong * 1024)()
+    assert _ext.load().bode_debug_prepare_tiles(buf) == 0
+    t = np.array(buf[:], dtype=np.int64).reshape(64, 16)[: min(64, a.S)]
+    names = ["setup+U+e", "gram", "cholesky", "scalars", "inverse", "w", "copy-out"]
+    dt = np.diff(t[:, :8], axis=1)
+    print("tile kernel, mean clk per section:", {n_: int(v) for n_, v in zip(names, dt.mean(axis=0))}, "total", int((t[:, 7] - t[:, 0]).mean()))
+    print("cholesky detail (sum over panels): update warp1 %d, update warp0 %d, diag factor+inverse warp0 %d, warp1 update+wait %d" % (
+        t[:, 8].mean(), t[:, 13].mean(), (t[:, 9] - t[:, 13]).mean(), t[:, 14].mean()))
+    sys.exit(0)
 buf = (ctypes.c_longlong * 512)()
 assert _ext.load().bode_debug_prepare(buf) == 0
 t = np.array(buf[:], dtype=np.int64).reshape(64, 8)[: min(64, a.S)]

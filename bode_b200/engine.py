@@ -222,9 +222,10 @@ class EkldEngine:
         return mu, sg
 
     # ---- K2-K4 ---------------------------------------------------------------------------------------------
-    def score(self, X_design, idx_offset=0, form=_ext.BODE_FORM_REFERENCE, want_var=True, timed=False, events=None):
+    def score(self, X_design, idx_offset=0, form=_ext.BODE_FORM_REFERENCE, want_var=True, timed=False, events=None,
+              want_logk=True):
         """Score every row of X_design (device or host array).  Returns device tensors:
-        dict(score (Nd,), var (Nd,)|None, logk (S, Nd), best (1,), best_idx (1,) int64, rec int64[2] = the packed
+        dict(score (Nd,), var (Nd,)|None, logk (S, Nd)|None, best (1,), best_idx (1,) int64, rec int64[2] = the packed
         16-byte (best, best_idx) record).  ``logk`` is a view of an engine-owned buffer, valid until the next call."""
         if not self._prepared:
             raise RuntimeError("call prepare() first")
@@ -235,12 +236,13 @@ class EkldEngine:
             Nd, d = Xd.shape
             if d != self.d:
                 raise ValueError("X_design has %d columns, observations have %d" % (d, self.d))
-            logk = self._buf("logk", self.S * Nd, torch.float64)[: self.S * Nd].view(self.S, Nd)
+            # want_logk=False: the per-sample matrix is not materialised (the kernels keep their two S x Nd planes in scratch)
+            logk = self._buf("logk", self.S * Nd, torch.float64)[: self.S * Nd].view(self.S, Nd) if want_logk else None
             score = torch.empty(Nd, dtype=torch.float64, device=self.device)
             var = torch.empty(Nd, dtype=torch.float64, device=self.device) if want_var else None
             rec = torch.empty(2, dtype=torch.int64, device=self.device)  # packed {float64 best, int64 best_idx}
             best, best_idx = rec[:1].view(torch.float64), rec[1:]
-            scr = self._buf("scratch", 256 + self.lib.bode_ekld_score_scratch_bytes(Nd, self.S), torch.uint8)
+            scr = self._buf("scratch", 256 + self.lib.bode_ekld_score_scratch_bytes(Nd, self.S if want_logk else 2 * self.S), torch.uint8)
             args = [_ptr(self.ws), self.n, self.d, self.S, _ptr(Xd), Nd, int(idx_offset), int(form), _ptr(logk),
                     _ptr(score), _ptr(var), _ptr(best), _ptr(best_idx), _ptr(scr), self._stream()]
             if self.quad is not None:

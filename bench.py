@@ -52,7 +52,7 @@ UNIT = "evals/s"
 CONFIGS = {
     "c3": dict(d=8, n=200, S=64, Nd=100000, Nq=0, seed=1223, nugget=1e-3, form=0, cpu_cand=40000, cpu_samp=64,
                name="config3: d=8 n=200 S=64 |X_design|=1e5 total (closed-form EKLD, dense scoring)"),
-    "c4": dict(d=10, n=500, S=128, Nd=1000000, Nq=0, seed=1223, nugget=1e-3, form=1, cpu_cand=4000, cpu_samp=32,
+    "c4": dict(d=10, n=500, S=128, Nd=1000000, Nq=0, seed=1223, nugget=1e-3, form=1, cpu_cand=16000, cpu_samp=128,
                name="config4: d=10 n=500 S=128 |X_design|=1e6 total (closed-form EKLD, log1p form, dense scoring)"),
     "c4quad": dict(d=10, n=500, S=128, Nd=1000000, Nq=100000, seed=1223, nugget=1e-3, form=1, cpu_cand=64, cpu_samp=16,
                    name="config4 quadrature mode: d=10 n=500 S=128 |X_design|=1e6 total, N_q=1e5 quadrature points"),

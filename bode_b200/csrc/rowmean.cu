@@ -5,10 +5,10 @@
 // There is no reference call site (the reference integrates in closed form); parity is against the oracle's own
 // quadrature variant on the same X_quad.
 //
-// One thread per point, one hyper-sample per blockIdx.y; quadrature points are staged through shared memory already
-// scaled by 1/(sqrt2 ell); each thread sums q = 0..Nq-1 into four interleaved accumulators (q mod 4) combined in a
-// fixed order, so the result does not depend on the launch geometry.  FP64-pipe bound: 2d + 12 operations per
-// (point, quadrature point) pair.
+// Two points per thread, one hyper-sample per blockIdx.y; quadrature points are staged through shared memory in the
+// scaled, centred coordinates of rbf.h (doubled, with -|v|^2 appended); each thread sums q = 0..Nq-1 into four interleaved
+// accumulators (q mod 4) combined in a fixed order, so the result does not depend on the launch geometry.  FP64-pipe
+// bound: d + 11 operations per (point, quadrature point) pair (GEMM-form distance + 9-operation table exp2).
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -20,40 +20,73 @@ namespace bode {
 
 constexpr int kRmThreads = 256;
 constexpr int kRmChunk = 512;  // quadrature points per shared-memory chunk
+constexpr int kRmPts = 2;      // points per thread (the staged quadrature rows are read once for both)
 
+// z = -|u_i|^2 - |v_q|^2 + 2 u_i . v_q in the scaled, centred coordinates of rbf.h (u = kappa c (p - 1/2)), the same
+// GEMM-form distance and 9-operation table exp2 as the scoring kernel's cross-covariance: d + 11 FP64 operations per
+// (point, quadrature point) pair instead of the 2d + 12 of direct differences + the 11-operation exp.
 template <int DP, bool WEIGHTED>
 __device__ __forceinline__ void rowmean_body(const double* __restrict__ P, int64_t Np, const double* __restrict__ Xq,
-                                             const double* __restrict__ wq, int Nq, int d, const double* ck,
+                                             const double* __restrict__ wq, int Nq, int d, const double* cku,
                                              const double* tab, double* qs, double* ws_, double scale, double* __restrict__ out) {
-  const int64_t i = (int64_t)blockIdx.x * kRmThreads + threadIdx.x;
-  double y[DP];
+  constexpr int DPAD = (DP + 2) & ~1;  // DP doubled coordinates + -|v|^2, padded to an even count (16-byte rows)
+  const double* tab_lane = tab + (threadIdx.x & (kTabRep - 1));  // bank-staggered table copies: conflict-free lookups
+  int64_t i[kRmPts];
+  double y[kRmPts][DP], nyn[kRmPts], acc[kRmPts][4];
 #pragma unroll
-  for (int k = 0; k < DP; k++) y[k] = (i < Np) ? P[i * d + k] * ck[k] : 0.0;
-  constexpr int DPAD = (DP + 1) & ~1;
-  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int p = 0; p < kRmPts; p++) {
+    i[p] = ((int64_t)blockIdx.x * kRmPts + p) * kRmThreads + threadIdx.x;
+    nyn[p] = 0.0;
+#pragma unroll
+    for (int k = 0; k < DP; k++) {
+      y[p][k] = (i[p] < Np) ? (P[i[p] * d + k] - 0.5) * cku[k] : 0.0;
+      nyn[p] = fma(-y[p][k], y[p][k], nyn[p]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[p][j] = 0.0;
+  }
   for (int q0 = 0; q0 < Nq; q0 += kRmChunk) {
     const int nq = min(kRmChunk, Nq - q0);
     __syncthreads();
-    for (int idx = threadIdx.x; idx < kRmChunk * DPAD; idx += kRmThreads) {
-      const int q = idx / DPAD, k = idx - q * DPAD;
-      qs[idx] = (q < nq && k < d) ? Xq[(size_t)(q0 + q) * d + k] * ck[k] : 0.0;
+    // staged row of quadrature point q: [2 v_0 .. 2 v_(DP-1), -|v|^2]; rows beyond nq: far away (k = 0 exactly after the clamp)
+    for (int q = threadIdx.x; q < kRmChunk; q += kRmThreads) {
+      double nv = 0.0;
+#pragma unroll
+      for (int k = 0; k < DP; k++) {
+        const double v = (q < nq) ? (Xq[(size_t)(q0 + q) * d + k] - 0.5) * cku[k] : 0.0;
+        qs[(size_t)q * DPAD + k] = 2.0 * v;
+        nv = fma(-v, v, nv);
+      }
+      qs[(size_t)q * DPAD + DP] = nv;
+      if (WEIGHTED) ws_[q] = (q < nq) ? wq[q0 + q] : 0.0;
     }
-    if (WEIGHTED)
-      for (int q = threadIdx.x; q < kRmChunk; q += kRmThreads) ws_[q] = (q < nq) ? wq[q0 + q] : 0.0;
     __syncthreads();
-    const int nq4 = (nq + 3) & ~3;  // padded rows contribute exp(-|y|^2) * 0 (weighted) or are masked below
+    const int nq4 = (nq + 3) & ~3;  // padded rows are masked below (unweighted) or carry weight 0 (weighted)
     for (int q = 0; q < nq4; q += 4) {
-      double kv[4];
 #pragma unroll
-      for (int j = 0; j < 4; j++) kv[j] = rbf_exp(-sqdist<DP>(qs + (size_t)(q + j) * DPAD, y), tab);
+      for (int p = 0; p < kRmPts; p++) {
+        double z[4], kv[4];
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        if (WEIGHTED) acc[j] = fma(ws_[q + j], kv[j], acc[j]);
-        else acc[j] += (q + j < nq) ? kv[j] : 0.0;
+        for (int j = 0; j < 4; j++) {
+          const double* row = qs + (size_t)(q + j) * DPAD;
+          double t = row[DP] + nyn[p];
+#pragma unroll
+          for (int k = 0; k < DP; k++) t = fma(y[p][k], row[k], t);
+          z[j] = fmin(t, 0.0);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) kv[j] = rbf_exp64<kTabRep>(z[j], tab_lane);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          if (WEIGHTED) acc[p][j] = fma(ws_[q + j], kv[j], acc[p][j]);
+          else acc[p][j] += (q + j < nq) ? kv[j] : 0.0;
+        }
       }
     }
   }
-  if (i < Np) out[i] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) * scale;
+#pragma unroll
+  for (int p = 0; p < kRmPts; p++)
+    if (i[p] < Np) out[i[p]] = ((acc[p][0] + acc[p][1]) + (acc[p][2] + acc[p][3])) * scale;
 }
 
 template <bool WEIGHTED>
@@ -63,15 +96,16 @@ __global__ void __launch_bounds__(kRmThreads) k_rowmean(const double* __restrict
                                                         int Nq, const double* __restrict__ wsum_ptr, double* __restrict__ out) {
   extern __shared__ __align__(16) double sm[];
   double* qs = sm;                               // [kRmChunk][dpad]
-  double* ws_ = qs + kRmChunk * ((d + 1) & ~1);  // [kRmChunk]
-  double* tab = ws_ + kRmChunk;                  // [32] exp table WITHOUT the variance (scale applied at the end)
-  double* ck = tab + kTabPad;                    // [16]
+  double* ws_ = qs + kRmChunk * ((d + 2) & ~1);  // [kRmChunk]
+  double* tab = ws_ + kRmChunk;                  // [64][16] 2^(j/64), each entry replicated 16 times (layout.h): WITHOUT the
+                                                 // variance (scale applied at the end)
+  double* cku = tab + kTab64 * kTabRep;          // [16] kappa / (sqrt2 ell_k)
   const int s = blockIdx.y;
   const double* h = hyp + (size_t)s * ndim;
-  if (threadIdx.x < kTabPad) tab[threadIdx.x] = exp2((double)threadIdx.x / 32.0);
-  if (threadIdx.x >= 32 && threadIdx.x < 32 + kCkPad) {
-    const int k = threadIdx.x - 32;
-    ck[k] = (k < d) ? 1.0 / (1.4142135623730951 * h[1 + k]) : 0.0;
+  for (int idx = threadIdx.x; idx < kTab64 * kTabRep; idx += kRmThreads) tab[idx] = exp2((double)(idx / kTabRep) / 64.0);
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + kCkPad) {
+    const int k = threadIdx.x - 64;
+    cku[k] = (k < d) ? kKappa / (1.4142135623730951 * h[1 + k]) : 0.0;
   }
   __syncthreads();
   const double scale = h[0] / (wsum_ptr ? wsum_ptr[0] : (double)Nq);
@@ -79,7 +113,7 @@ __global__ void __launch_bounds__(kRmThreads) k_rowmean(const double* __restrict
   switch (d) {
 #define BODE_CASE(D)                                                                            \
   case D:                                                                                       \
-    rowmean_body<D, WEIGHTED>(P, Np, Xq, wq, Nq, d, ck, tab, qs, ws_, scale, o);                \
+    rowmean_body<D, WEIGHTED>(P, Np, Xq, wq, Nq, d, cku, tab, qs, ws_, scale, o);               \
     break;
     BODE_CASE(1) BODE_CASE(2) BODE_CASE(3) BODE_CASE(4) BODE_CASE(5) BODE_CASE(6) BODE_CASE(7) BODE_CASE(8)
     BODE_CASE(9) BODE_CASE(10) BODE_CASE(11) BODE_CASE(12) BODE_CASE(13) BODE_CASE(14) BODE_CASE(15) BODE_CASE(16)
@@ -115,16 +149,16 @@ __global__ void __launch_bounds__(256) k_sum_weights(const double* __restrict__ 
 
 cudaError_t launch_rowmean(const double* hyp, int S, int ndim, int d, const double* P, int64_t Np, const double* Xq,
                            const double* wq, int Nq, const double* wsum_ptr, double* out, cudaStream_t st) {
-  const int dpad = (d + 1) & ~1;
-  const size_t smem = sizeof(double) * ((size_t)kRmChunk * dpad + kRmChunk + kTabPad + kCkPad);
-  const dim3 grid((unsigned)((Np + kRmThreads - 1) / kRmThreads), (unsigned)S);
-  // (the largest configuration, d = 16, needs 72 KB: opt in once per device)
+  const int dpad = (d + 2) & ~1;
+  const size_t smem = sizeof(double) * ((size_t)kRmChunk * dpad + kRmChunk + kTab64 * kTabRep + kCkPad);
+  const dim3 grid((unsigned)((Np + (int64_t)kRmThreads * kRmPts - 1) / ((int64_t)kRmThreads * kRmPts)), (unsigned)S);
+  // (the largest configuration, d = 16, needs 78 KB: opt in once per device)
   static thread_local int attr_dev = -1;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (dev != attr_dev) {
-    const int max_smem = (int)(sizeof(double) * ((size_t)kRmChunk * 16 + kRmChunk + kTabPad + kCkPad));
+    const int max_smem = (int)(sizeof(double) * ((size_t)kRmChunk * 18 + kRmChunk + kTab64 * kTabRep + kCkPad));
     e = cudaFuncSetAttribute(k_rowmean<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_rowmean<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);

@@ -26,9 +26,12 @@ def dette8(x):
 
 
 def ex4_func6(x):
-    """6-D test function of reference tests/samp_ex4.py:28-39 (noise-free)."""
+    """6-D test function of reference tests/samp_ex4.py:28-39 (`Ex1Func`, noise-free): a scaled DTLZ-type function from
+    Knowles (2006): g = 100 (sum_{i=1..5} ((x_i - 1/2)^2 - cos(2 pi (x_i - 1/2))) + 5), k = (1 - x_0) (g + 1) / 2, (k - 150) / 80."""
     x = np.asarray(x, dtype=float)
-    return float(np.sum(np.sin(3 * x) * np.arange(1, x.shape[0] + 1)) / 6.0 + np.prod(x[:3]))
+    g = 100. * (((x[1:6] - 0.5) ** 2 - np.cos(2. * np.pi * (x[1:6] - 0.5))).sum() + 5.)
+    k = 0.5 * (1 - x[0]) * (g + 1.)
+    return float((k - 150.) / 80.)
 
 
 def make_problem(d, n, S, Nd, seed, ell_lo=0.15, ell_hi=0.9, var_shape=2.0, noisy=False, objective=None):

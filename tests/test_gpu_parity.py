@@ -576,6 +576,24 @@ def test_example_driver_outputs(tmp_path):
     assert -2.0 < mu[-1] < -0.8
 
 
+@pytest.mark.parametrize("script,shape", [("dette.py", (202, 8)), ("samp_ex4.py", (23, 6))])
+def test_named_config_drivers_run(tmp_path, script, shape):
+    """examples/dette.py (BASELINE config 3: 8-D Dette-Pepelyshev, n = 200, 64 hyper-samples; 2e4 designs here) and
+    examples/samp_ex4.py (config 5's 6-D function, 1e4 designs) with short chains: real host MCMC with device likelihoods, a
+    few iterations of the loop, artefacts in the reference drivers' formats."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "run")
+    cmd = [sys.executable, os.path.join(root, "examples", script), "--quick", "--out", out]
+    if script == "dette.py":
+        cmd += ["--designs", "20000"]
+    subprocess.check_call(cmd, timeout=900, stdout=subprocess.DEVNULL)
+    X = np.load(os.path.join(out, "X.npy")); kld = np.load(os.path.join(out, "kld.npy")); mu = np.load(os.path.join(out, "mu_qoi.npy"))
+    assert X.shape == shape and kld.shape[0] == shape[0] - (200 if script == "dette.py" else 20)
+    assert np.isfinite(kld).all() and (kld > 0).all() and len(mu) == kld.shape[0] + 1 and np.isfinite(mu).all()
+
+
 # ---- quadrature mode (north star: k(X_design, X_quad), k(X, X_quad) averaged over quadrature points) --------------------
 @pytest.mark.parametrize("weighted", [False, True])
 def test_quad_mode_parity(engine, weighted):

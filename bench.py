@@ -321,8 +321,13 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nd", type=int, default=0, help="developer: override |X_design| (e.g. one rank's shard of an 8-GPU run on one GPU)")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
+    if args.nd:
+        cfg["Nd"] = args.nd
+        cfg["cpu_cand"] = min(cfg.get("cpu_cand", args.nd), args.nd)
+        cfg["name"] += " [developer override: |X_design|=%d]" % args.nd
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference(args, cfg)
@@ -426,9 +431,18 @@ def bench_dense(args, cfg, eng, world, rank, local_rank, barrier, cpu_pool):
     info = eng.prepare(X, Y, hyp, nug2, quad=qdev)
     assert int(info.abs().max()) == 0, "synthetic hyper-samples must all factorise"
 
-    # ---- device-resident arm ----
+    # ---- device-resident arm: the step as one captured CUDA graph (EkldEngine / StepGraph public API) ----
+    from bode_b200.engine import StepGraph
+    use_graph = quad is None
+    sg = StepGraph(eng, hX, hY, hH, Xd_dev, nug2, idx_offset=lo, form=form) if use_graph else None
+
+    def timed_step():
+        if sg is not None:
+            return sg.run(), sg.out
+        return step_resident()
+
     for _ in range(args.warmup):
-        step_resident()
+        timed_step()
         flush.zero_()
     clocks = ClockSampler(local_rank) if rank == 0 else None
     if clocks:
@@ -436,22 +450,17 @@ def bench_dense(args, cfg, eng, world, rank, local_rank, barrier, cpu_pool):
         time.sleep(0.3)
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    # event pairs the C ABI records around the scoring kernel (no synchronisation inside the timed region)
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for a_, b_ in kev:
-        a_.record(); b_.record()
     torch.cuda.synchronize()
     wall0 = time.perf_counter()
     best = None
     for i in range(args.steps):
         flush.zero_()  # L2 flush between timed iterations (outside the per-step event pair)
         ev[i][0].record()
-        best, r_last = step_resident(events=None if quad is not None else kev[i])
+        best, r_last = timed_step()
         ev[i][1].record()
     barrier()
     wall = time.perf_counter() - wall0
     step_ms = [a.elapsed_time(b) for a, b in ev]
-    kernel_ms = [a_.elapsed_time(b_) for a_, b_ in kev]
     t_local = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         tdist.all_reduce(t_local, op=tdist.ReduceOp.MAX)
@@ -459,10 +468,30 @@ def bench_dense(args, cfg, eng, world, rank, local_rank, barrier, cpu_pool):
     value = Nd * S / (ms_per_step * 1e-3)
     score_gpu = r_last["score"].cpu().numpy() if rank == 0 else None  # rank 0's shard starts at candidate 0
 
+    # ---- the dominant kernel's own duration: event pairs the C ABI records around k_score (plain launches, L2 flushed) ----
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 5))]
+    for a_, b_ in kev:
+        a_.record(); b_.record()
+    torch.cuda.synchronize()
+    if quad is None:
+        for a_b in kev:
+            flush.zero_()
+            bk_, _ = step_resident(events=a_b)
+            assert bk_[1] == best[1]
+    torch.cuda.synchronize()
+    kernel_ms = [a_.elapsed_time(b_) for a_, b_ in kev]
+
     # ---- end-to-end arm: host buffers in, host results out, every step ----
     h_score = torch.empty(hi - lo, dtype=torch.float64).pin_memory()
+    sg2 = StepGraph(eng, hX, hY, hH, hXd, nug2, idx_offset=lo, form=form) if use_graph else None
 
     def step_e2e():
+        if sg2 is not None:
+            sg2.launch()
+            h_score.copy_(sg2.out["score"], non_blocking=True)
+            b = sg2.winner()
+            torch.cuda.synchronize()
+            return b
         eng.prepare(hX.to(dev, non_blocking=True), hY.to(dev, non_blocking=True), hH.to(dev, non_blocking=True), nug2, quad=qdev)
         r = eng.score(hXd.to(dev, non_blocking=True), idx_offset=lo, form=form, want_var=False, want_logk=False)
         h_score.copy_(r["score"], non_blocking=True)
@@ -546,6 +575,7 @@ def bench_dense(args, cfg, eng, world, rank, local_rank, barrier, cpu_pool):
                    "step": "prepare (S Cholesky, tensor pipe) + k_score over the rank's candidates (sigma_x, w.k) + xik/EKLD/log + in-order "
                            "reduction over hyper-samples + argmax" + (" + one 16-byte ncclAllGather (C ABI)" if world > 1 else ""),
                    "l2": "flushed between timed iterations (256 MB write)",
+                   "launch": "the step's copies and kernels are captured once into a CUDA graph (bode_b200.engine.StepGraph) and replayed" if use_graph else "plain launches",
                    "sharding": "fixed design of %d candidates split into contiguous blocks of %d per rank" % (Nd, hi - lo),
                    "ekld_form": "reference expression (_sampler.py:480)" if form == 0 else "log1p form (analytically identical)",
                    "wall_s_timed_region": wall},
@@ -563,7 +593,8 @@ def bench_dense(args, cfg, eng, world, rank, local_rank, barrier, cpu_pool):
         "cpu_baseline": cpu,
         "parity": parity,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": launches,  # k_prepare (+ xik series blocks), k_score, k_ekld_reduce (+ final argmax) per step
+        "gpu_launches": launches,  # k_prepare_tiles (+ xik series blocks), k_score, k_ekld_reduce (+ final argmax) per step,
+                                   # replayed from one captured CUDA graph
         "clocks": clock_info,
         "best_idx": best[1],
     }

@@ -353,7 +353,7 @@ int bode_ekld_mu_sigma_dev(const void* workspace, int n, int d, int S, double* o
 // scratch = [done counter: 256 B] [block argmax values] [block argmax indices] [w.k plane: S*Nd] [sigma_x plane: S*Nd, only
 // when the caller passes no logk buffer]
 static size_t score_partials_bytes(int64_t Nd) {
-  const size_t nb = (size_t)((Nd + 63) / 64);  // an upper bound for both reduction kernels' block counts
+  const size_t nb = (size_t)((Nd + 31) / 32);  // an upper bound for both reduction kernels' block counts
   return 256 + align_up(nb * sizeof(double), 256) + align_up(nb * sizeof(int64_t), 256);
 }
 
@@ -377,7 +377,7 @@ static int score_common(const void* workspace, int n, int d, int S, const double
   const Layout L = make_layout(n, d, S);
   if (plan_score(L, Nd, props.sm_count, props.smem_optin, &P) != 0) return BODE_ERR_UNSUPPORTED;
   char* scr = static_cast<char*>(scratch);
-  const size_t nb = (size_t)((Nd + 63) / 64);
+  const size_t nb = (size_t)((Nd + 31) / 32);
   unsigned int* done_counter = reinterpret_cast<unsigned int*>(scr);
   double* part_val = reinterpret_cast<double*>(scr + 256);
   int64_t* part_idx = reinterpret_cast<int64_t*>(scr + 256 + align_up(nb * sizeof(double), 256));

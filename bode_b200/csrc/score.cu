@@ -602,8 +602,6 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
 // hyper-samples is exactly the sequential s = 0..S-1 sum the oracle defines, independent of tiling, sharding and
 // launch geometry.
 // ----------------------------------------------------------------------------------------------------------------
-constexpr int kErCpl = 2;                 // candidates per lane (independent dependency chains per thread)
-constexpr int kErCand = 32 * kErCpl;      // candidates per block
 constexpr int kErWarps = 8;               // hyper-samples in flight per block
 
 __device__ __forceinline__ bool better(double av, int64_t ai, double bv, int64_t bi) {
@@ -662,6 +660,8 @@ __device__ __forceinline__ void final_argmax(double bv, int64_t bi, double* part
   }
 }
 
+// kErCpl: candidates per lane (independent dependency chains per thread; 1 for small designs so that the grid still covers the SMs)
+template <int kErCpl>
 __global__ void __launch_bounds__(32 * kErWarps) k_ekld_reduce(const char* __restrict__ ws, Layout L, const double* __restrict__ Xd,
                                                                const double* __restrict__ xi_ovr, double* __restrict__ sx,
                                                                const double* __restrict__ wkplane, int S, int64_t Nd,
@@ -670,6 +670,7 @@ __global__ void __launch_bounds__(32 * kErWarps) k_ekld_reduce(const char* __res
                                                                double* __restrict__ part_val, int64_t* __restrict__ part_idx,
                                                                unsigned int* __restrict__ done_counter,
                                                                double* __restrict__ best, int64_t* __restrict__ best_idx) {
+  constexpr int kErCand = 32 * kErCpl;              // candidates per block
   extern __shared__ __align__(16) double xc_all[];  // [kErWarps][d][kXcStride]: series of the xik factors, one sample per warp
   __shared__ double lkbuf[2][kErWarps][kErCand];    // log EKLD (then squared deviations) on their way to warp 0
   __shared__ double meanbuf[kErCand];
@@ -1066,20 +1067,29 @@ cudaError_t launch_ekld_reduce(const void* ws, const Layout& L, const double* Xd
                                const double* wkplane, int S, int64_t Nd, int64_t idx_offset, int form, int keep_logk,
                                double* score, double* var, double* part_val, int64_t* part_idx, unsigned int* done_counter,
                                double* best, int64_t* best_idx, cudaStream_t st) {
-  const int nb = (int)((Nd + kErCand - 1) / kErCand);
+  const int cpl = Nd >= 64 * 148 * 2 ? 2 : 1;  // small designs: one candidate per lane, twice the blocks
+  const int nb = (int)((Nd + 32 * cpl - 1) / (32 * cpl));
   const size_t smem = sizeof(double) * kErWarps * (size_t)L.d * kXcStride;  // 25.6 KB at d = 8, 51.2 KB at d = 16
   static thread_local int attr_dev = -1;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (dev != attr_dev) {  // d = 16 needs more than the 48 KB default: opt in once per device
-    e = cudaFuncSetAttribute(k_ekld_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * kErWarps * 16 * kXcStride));
+    const int max_smem = (int)(sizeof(double) * kErWarps * 16 * kXcStride);
+    e = cudaFuncSetAttribute(k_ekld_reduce<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_ekld_reduce<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     if (e != cudaSuccess) return e;
     attr_dev = dev;
   }
-  k_ekld_reduce<<<nb, 32 * kErWarps, smem, st>>>(static_cast<const char*>(ws), L, Xd, xi_ovr, sx, wkplane, S, Nd, idx_offset, form,
-                                                 tuning().xik_series, keep_logk || var != nullptr, score, var, part_val, part_idx,
-                                                 done_counter, best, best_idx);
+  if (cpl == 2)
+    k_ekld_reduce<2><<<nb, 32 * kErWarps, smem, st>>>(static_cast<const char*>(ws), L, Xd, xi_ovr, sx, wkplane, S, Nd, idx_offset, form,
+                                                      tuning().xik_series, keep_logk || var != nullptr, score, var, part_val, part_idx,
+                                                      done_counter, best, best_idx);
+  else
+    k_ekld_reduce<1><<<nb, 32 * kErWarps, smem, st>>>(static_cast<const char*>(ws), L, Xd, xi_ovr, sx, wkplane, S, Nd, idx_offset, form,
+                                                      tuning().xik_series, keep_logk || var != nullptr, score, var, part_val, part_idx,
+                                                      done_counter, best, best_idx);
   return cudaGetLastError();
 }
 

@@ -288,6 +288,58 @@ class EkldEngine:
         return dict(pred_var=pv, sigma_x=sigx, best=best, best_idx=best_idx)
 
 
+class StepGraph(object):
+    """One outer-iteration step -- copy X, Y, hyp (and, if it lives on the host, the design block) to the device, prepare,
+    score, and on several GPUs the 16-byte argmax all-gather -- captured ONCE into a CUDA graph and replayed: a step then
+    costs one graph launch instead of half a dozen host-side launches, which is what a 12 500-candidate shard of an 8-GPU
+    run is otherwise bound by.  The tensors passed in are read at every replay (update them in place: pinned host
+    tensors for X, Y, hyp, the design wherever it lives); results are the engine-owned tensors of ``self.out``.
+
+        sg = StepGraph(engine, hX, hY, hH, Xd, nugget_var, idx_offset=lo)
+        best, idx = sg.run()          # replay + one small device->host read (the winner)
+    """
+
+    def __init__(self, engine, X, Y, hyp, X_design, nugget_var, idx_offset=0, form=_ext.BODE_FORM_REFERENCE, quad=None,
+                 want_var=False, want_logk=False, jitter=GPY_JITTER):
+        self.eng = engine
+        dev = engine.device
+
+        def body():
+            to = lambda t: t.to(dev, non_blocking=True) if isinstance(t, torch.Tensor) else t
+            engine.prepare(to(X), to(Y), to(hyp), nugget_var, jitter, quad=quad)
+            r = engine.score(to(X_design), idx_offset=idx_offset, form=form, want_var=want_var, want_logk=want_logk)
+            if engine._comm is not None:
+                _ext.check(engine.lib.bode_ekld_argmax_nccl(engine._comm, _ptr(r["rec"]), _ptr(engine._gathered), engine._stream()))
+            return r
+
+        with torch.cuda.device(dev):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):  # warm-up outside the capture: function attributes, allocator pools, NCCL channels
+                for _ in range(2):
+                    body()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = body()
+
+    def launch(self):
+        """Enqueue the step (no host synchronisation); results land in ``self.out`` / the engine's gather buffer."""
+        self.graph.replay()
+
+    def winner(self):
+        """(best score, global index) after ``launch``: one device->host copy, np.argmax semantics across ranks."""
+        if self.eng._comm is not None:
+            return _ext.argmax_combine(self.eng._gathered.cpu().numpy())
+        rec = self.out["rec"].cpu()
+        return float(rec[:1].view(torch.float64).item()), int(rec[1].item())
+
+    def run(self):
+        self.launch()
+        return self.winner()
+
+
 def ekld_score(X, Y, hyp, X_design, nugget=1e-3, jitter=GPY_JITTER, form=_ext.BODE_FORM_REFERENCE, engine=None,
                want_kld=False, quad=None):
     """One-call public API with host (NumPy) buffers: prepare + score + summary, results back on the host.

@@ -447,6 +447,28 @@ def test_prepare_kernel_variants_agree(engine, ext, n, d, monkeypatch):
     engine.prepare(X, Y, hyp, 1e-6)
 
 
+def test_step_graph_replays_match_plain_calls(engine):
+    """StepGraph: the step (copies + prepare + score) captured once into a CUDA graph; replays read the pinned host inputs
+    again, so updating them in place gives the next iteration's result -- bit-identical to plain calls."""
+    import torch
+    from bode_b200.engine import StepGraph
+    X, Y, Xd, hyp = cases.make_problem(5, 40, 6, 2000, seed=91, ell_lo=0.2, ell_hi=0.8)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).pin_memory()
+    hX, hY, hH, hXd = pin(X), pin(Y), pin(hyp), pin(Xd)
+    sg = StepGraph(engine, hX, hY, hH, hXd, 1e-6, idx_offset=7, want_var=True)
+    for trial in range(3):
+        best, idx = sg.run()
+        got = sg.out["score"].cpu().numpy().copy(); gvar = sg.out["var"].cpu().numpy().copy()
+        engine.prepare(hX.numpy(), hY.numpy(), hH.numpy(), 1e-6)
+        ref = engine.score(hXd.numpy(), idx_offset=7)
+        np.testing.assert_array_equal(got, ref["score"].cpu().numpy())
+        np.testing.assert_array_equal(gvar, ref["var"].cpu().numpy())
+        assert idx == int(ref["best_idx"].item()) == 7 + int(np.argmax(got)) and best == float(ref["best"].item())
+        hH.mul_(1.07)                                  # next "iteration": new hyper-samples, new observations, in place
+        hY.add_(0.01 * (trial + 1))
+    engine.prepare(X, Y, hyp, 1e-6)
+
+
 def test_invalid_hyperparameters_are_rejected(ext):
     X, Y, Xd, hyp = cases.make_problem(2, 10, 3, 20, seed=2)
     hyp[1, 1] = -0.3   # negative lengthscale

@@ -737,6 +737,7 @@ __global__ void __launch_bounds__(32 * kErWarps) k_ekld_reduce(const char* __res
               b1[q] = 0.0;
               b2[q] = 0.0;
             }
+#pragma unroll 4
             for (int j = n - 1; j >= 1; j--) {
               const double aj = a[1 + j];
 #pragma unroll

@@ -54,6 +54,7 @@ static Tuning read_tuning() {
   t.stagger = geti("BODE_STAGGER", 0);
   t.xik_series = geti("BODE_XIK_SERIES", 1);
   t.prep_variant = geti("BODE_PREP_VARIANT", -1);
+  t.rowmean_variant = geti("BODE_ROWMEAN_VARIANT", -1);
   return t;
 }
 static Tuning g_tuning = read_tuning();

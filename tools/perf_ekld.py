@@ -12,7 +12,7 @@ from bode_b200.engine import EkldEngine  # noqa: E402
 
 
 def main():
-    w = bench.WORKLOAD
+    w = bench.CONFIGS["c3"]
     X, Y, hyp, Xd = bench.make_workload(w["d"], w["n"], w["S"], w["Nd"], w["seed"])
     eng = EkldEngine()
     eng.prepare(X, Y, hyp, w["nugget"] ** 2)

@@ -5,11 +5,12 @@ One "step" = one pass of the hot path over one batch of synthetic input: prepare
 on the tensor pipe) + dense scoring of every candidate of this rank's shard + closed-form EKLD, in-order reduction over
 hyper-samples and argmax (+ the 16-byte NCCL exchange when N > 1).  Prints ONE JSON line (rank 0).
 
-  python bench.py [--config c3|c4|c4quad|c5] [--gpus N --steps K --warmup W]     # our arm (default config: c3)
+  python bench.py [--config c2|c3|c4|c4quad|c5] [--gpus N --steps K --warmup W]  # our arm (default config: c3)
   python bench.py --impl reference [--config ...] [--gpus N ...]                 # CPU arm: the oracle port of the reference path
   torchrun --nproc-per-node N ... bench.py --gpus N ...                          # N > 1: one rank per GPU, candidate blocks sharded
 
 Configurations (BASELINE.json `configs`)
+  c2      d=2  n=30  S=32  |X_design|=1e4, closed-form EKLD: launch-latency / transcendental bound, report the absolute time
   c3      d=8  n=200 S=64  |X_design|=1e5 TOTAL, closed-form EKLD (the headline; "scaling": "strong" -- the design is fixed and
           split over the ranks; a weak-scaling side figure, 1e5 candidates per rank, is attached when N > 1)
   c4      d=10 n=500 S=128 |X_design|=1e6 total, closed-form EKLD (log1p form: at 1.28e8 evaluations the literal expression's
@@ -50,6 +51,8 @@ sys.path.insert(0, ROOT)
 METRIC = "ekld_candidate_evals_per_sec"
 UNIT = "evals/s"
 CONFIGS = {
+    "c2": dict(d=2, n=30, S=32, Nd=10000, Nq=0, seed=1263, nugget=1e-3, form=0, cpu_cand=10000, cpu_samp=32,
+               name="config2: d=2 n=30 S=32 |X_design|=1e4 (closed-form EKLD, dense scoring; launch-latency bound: absolute time)"),
     "c3": dict(d=8, n=200, S=64, Nd=100000, Nq=0, seed=1223, nugget=1e-3, form=0, cpu_cand=40000, cpu_samp=64,
                name="config3: d=8 n=200 S=64 |X_design|=1e5 total (closed-form EKLD, dense scoring)"),
     "c4": dict(d=10, n=500, S=128, Nd=1000000, Nq=0, seed=1223, nugget=1e-3, form=1, cpu_cand=16000, cpu_samp=128,
@@ -75,6 +78,8 @@ def make_workload(d, n, S, Nd, seed, rank=0):
     X = rng.random((n, d))
     Y = cases.dette8(X)[:, None] if d == 8 else (np.sin(3 * X.sum(1)) + X[:, 0] ** 2)[:, None]
     hyp = np.column_stack([rng.gamma(1.0, 2.0, S) + 0.05] + [np.maximum(rng.exponential(0.7, S), 0.05) for _ in range(d)])
+    if n <= 64:  # few observations: keep the prior draws well conditioned (reject cond(A) > 1e6 -> cap ell)
+        hyp[:, 1:] = np.minimum(hyp[:, 1:], 0.6)
     rng_c = np.random.default_rng(seed + 1000 * (rank + 1))
     Xd = rng_c.random((Nd, d))
     return X, Y, hyp, Xd

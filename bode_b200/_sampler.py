@@ -85,7 +85,8 @@ class KLSampler(object):
                  ekld_form=1,
                  hyper_samples=None,
                  process_group=None,
-                 ekld_mode='closed'):
+                 ekld_mode='closed',
+                 ekld_form_check=None):
         X = np.asarray(X, dtype=np.float64)
         Y = np.asarray(Y, dtype=np.float64)
         assert X.ndim == 2
@@ -130,6 +131,11 @@ class KLSampler(object):
         self._ego_seq = (1 - ego_init_perc) * self.ego_iter
         self.X_design = None if X_design is None else np.ascontiguousarray(X_design, dtype=np.float64)
         self.ekld_form = ekld_form
+        # ekld_form=1 is a deliberate behaviour change at the boundary (module docstring): make it loud.  When the check is
+        # on, every scoring call also evaluates the reference's literal expression and prints one line if the chosen design
+        # differs (or the literal form produced NaN / -inf scores).  Default: on while it is cheap (N_d * S <= 2e6), off for
+        # large dense designs unless requested.
+        self.ekld_form_check = ekld_form_check
         if ekld_mode not in ('closed', 'quad'):
             raise ValueError("ekld_mode must be 'closed' (reference closed-form integrals) or 'quad' (quadrature points)")
         self.ekld_mode = ekld_mode
@@ -312,8 +318,19 @@ class KLSampler(object):
         model = self.model if model is None else model
         self._prepare(model, self.X, self.Y)
         mu, sigma = self.engine.mu_sigma()
-        res = _dist.sharded_score(self.engine, X_design, form=self.ekld_form, group=self.process_group if self._sharded else None)
+        group = self.process_group if self._sharded else None
+        res = _dist.sharded_score(self.engine, X_design, form=self.ekld_form, group=group)
         res.update(mu=mu, sigma=sigma)
+        check = self.ekld_form_check
+        if check is None:
+            check = np.asarray(X_design).shape[0] * np.asarray(model[0]).shape[0] <= 2e6
+        if self.ekld_form == 1 and check:
+            lit = _dist.sharded_score(self.engine, X_design, form=0, group=group, want_var=False)
+            bad = int(np.sum(~np.isfinite(lit["score"])))
+            if bad or lit["idx_best"] != res["idx_best"]:
+                print('>... WARNING: ekld_form=1 (log1p form) selects design %d; the reference expression (_sampler.py:480) selects %d'
+                      ' (%d candidate scores are NaN/-inf under its 2e-16 noise floor)' % (res["idx_best"], lit["idx_best"], bad))
+            res["idx_best_literal"] = lit["idx_best"]
         return res
 
     def update_XY(self, x_best, y_obs):

@@ -257,3 +257,29 @@ runpy.run_path(%r, run_name="__main__")
     with open(out / "comp.pkl", "rb") as f:
         mu_us, sigma_us, models, models_us = pickle.load(f)
     assert len(mu_us) == 2 and models[0][0].shape == (60, 2)
+
+
+def test_log1p_form_default_is_loud_when_it_changes_the_choice(capsys):
+    """the drop-in class evaluates the log1p form by default; when that changes the chosen design against the
+    reference's literal expression, it says so."""
+    from tests.fake_engine import OracleEngine
+
+    class TwoFaced(OracleEngine):          # literal form (0) and log1p form (1) disagree on purpose
+        def score(self, X_design, idx_offset=0, form=0, want_var=True, **kw):
+            r = super().score(X_design, idx_offset=idx_offset, form=form, want_var=want_var, **kw)
+            if form == 0:
+                j = (int(torch.argmax(r["score"])) + 1) % r["score"].numel()   # a NaN next to the true winner
+                sc = r["score"].clone(); sc[j] = float("nan")
+                r.update(score=sc, best=sc[j:j + 1].clone(), best_idx=torch.tensor([idx_offset + j]))
+            return r
+
+    hyp = np.array([[1.0, 0.3], [2.0, 0.4]])
+    kls = _tiny_sampler(TwoFaced(), hyp)
+    res = kls.score_designs(np.linspace(0.05, 0.95, 12)[:, None])
+    out = capsys.readouterr().out
+    assert "WARNING: ekld_form=1" in out and res["idx_best_literal"] == (res["idx_best"] + 1) % 12
+    quiet = _tiny_sampler(OracleEngine(), hyp)
+    quiet.score_designs(np.linspace(0.05, 0.95, 12)[:, None])
+    assert "WARNING" not in capsys.readouterr().out
+    off = _tiny_sampler(TwoFaced(), hyp, ekld_form_check=False)
+    assert "idx_best_literal" not in off.score_designs(np.linspace(0.05, 0.95, 12)[:, None])

@@ -154,12 +154,12 @@ cudaError_t debug_copy_timeline(long long* host /* 8*16*16*10 */) {
 // kk + 4 * n with  n = q + 4e  for tile column 2q + e -- a fixed permutation of the 8 candidates of a tile that makes
 // these stores conflict-free (the accumulator column n of phase B belongs to tile column 2 (n & 3) + (n >> 2)).
 // ----------------------------------------------------------------------------------------------------------------
+// first half of a batch: fragment loads and the distance DMMAs of NB row tiles -> z (two columns per lane and tile), w
 template <int DK, int NB>
-__device__ __forceinline__ void phase_a_batch(const double2* __restrict__ nw, const double* __restrict__ ut_lane, int R, int rstride,
-                                              int r, const double (&yb)[DK], const double (&nyn)[2],
-                                              unsigned tab_lane, double (&wk)[2], double* __restrict__ kst,
-                                              int kstride DBG_PARAM) {
-  double acc[NB][2], wv[NB], af[NB][DK];
+__device__ __forceinline__ void pa_load_dmma(const double2* __restrict__ nw, const double* __restrict__ ut_lane, int R, int rstride,
+                                             int r, const double (&yb)[DK], const double (&nyn)[2], double (&acc)[NB][2],
+                                             double (&wv)[NB] DBG_PARAM) {
+  double af[NB][DK];
 #pragma unroll
   for (int t = 0; t < NB; t++) {
     const int Rt = R + t * rstride;
@@ -180,8 +180,14 @@ __device__ __forceinline__ void phase_a_batch(const double2* __restrict__ nw, co
 #ifdef BODE_TIMELINE
       if (dbg & 8) { acc[t][0] += af[t][i]; continue; }
 #endif
-      dmma884_ordered(acc[t][0], acc[t][1], af[t][i], yb[i]);
+      dmma884(acc[t][0], acc[t][1], af[t][i], yb[i]);
     }
+}
+
+// second half: k = variance 2^(z/64), the partial w.k and the stores into the Kc tile
+template <int NB>
+__device__ __forceinline__ void pa_exp_store(const double (&acc)[NB][2], const double (&wv)[NB], int R, int rstride,
+                                             unsigned tab_lane, double (&wk)[2], double* __restrict__ kst, int kstride DBG_PARAM) {
   double kv[2 * NB];
 #ifdef BODE_TIMELINE
   if (dbg & 16) { for (int i = 0; i < 2 * NB; i++) kv[i] = (&acc[0][0])[i]; } else
@@ -198,6 +204,16 @@ __device__ __forceinline__ void phase_a_batch(const double2* __restrict__ nw, co
     dst[0] = kv[2 * t];
     dst[16] = kv[2 * t + 1];
   }
+}
+
+template <int DK, int NB>
+__device__ __forceinline__ void phase_a_batch(const double2* __restrict__ nw, const double* __restrict__ ut_lane, int R, int rstride,
+                                              int r, const double (&yb)[DK], const double (&nyn)[2],
+                                              unsigned tab_lane, double (&wk)[2], double* __restrict__ kst,
+                                              int kstride DBG_PARAM) {
+  double acc[NB][2], wv[NB];
+  pa_load_dmma<DK, NB>(nw, ut_lane, R, rstride, r, yb, nyn, acc, wv DBG_ARG);
+  pa_exp_store<NB>(acc, wv, R, rstride, tab_lane, wk, kst, kstride DBG_ARG);
 }
 
 template <int DK, int C, int RG, int CT>
@@ -241,7 +257,24 @@ __device__ __forceinline__ void phase_a(const double* __restrict__ aux, const do
 #endif
   constexpr int NB = BODE_PA_NB;
   int R = rs;
-  for (; R + (NB - 1) * NRS < nrt; R += NB * NRS) phase_a_batch<DK, NB>(nw, ut_lane, R, NRS, r, yb, nyn, tab_lane, wk, kst, kstride DBG_ARG);
+  // software pipeline over the batches: the fragment loads and distance DMMAs of batch i+1 are issued before the
+  // exponentials of batch i, so that the 52-cycle DMMA latency and the shared-memory round trips of one batch hide behind
+  // the FP64 work of the other (phase A was latency-bound: 57 % pipe-busy with both warps of a scheduler in it)
+  if (R + (NB - 1) * NRS < nrt) {
+    double za[NB][2], wa[NB];
+    pa_load_dmma<DK, NB>(nw, ut_lane, R, NRS, r, yb, nyn, za, wa DBG_ARG);
+    int Rn = R + NB * NRS;
+    for (; Rn + (NB - 1) * NRS < nrt; Rn += NB * NRS) {
+      double zb[NB][2], wb[NB];
+      pa_load_dmma<DK, NB>(nw, ut_lane, Rn, NRS, r, yb, nyn, zb, wb DBG_ARG);
+      pa_exp_store<NB>(za, wa, R, NRS, tab_lane, wk, kst, kstride DBG_ARG);
+#pragma unroll
+      for (int t = 0; t < NB; t++) { za[t][0] = zb[t][0]; za[t][1] = zb[t][1]; wa[t] = wb[t]; }
+      R = Rn;
+    }
+    pa_exp_store<NB>(za, wa, R, NRS, tab_lane, wk, kst, kstride DBG_ARG);
+    R = Rn;
+  }
   int left = (R < nrt) ? (nrt - R + NRS - 1) / NRS : 0;
   if (NB > 4) {
     while (left >= 4) { phase_a_batch<DK, 4>(nw, ut_lane, R, NRS, r, yb, nyn, tab_lane, wk, kst, kstride DBG_ARG); R += 4 * NRS; left -= 4; }

@@ -25,7 +25,7 @@ EXPORTS = (
     "bode_ekld_prepare_quad_dev", "bode_ekld_score_quad_dev", "bode_ekld_score_host", "bode_gp_loglik_host", "bode_gp_loglik_dev", "bode_ekld_plan_describe", "bode_fp64_peak",
     "bode_tuning_reload", "bode_ctx_create", "bode_ctx_destroy", "bode_ctx_alloc_count", "bode_ekld_score_host_ctx", "bode_gp_loglik_host_ctx",
     "bode_nccl_unique_id", "bode_nccl_comm_create", "bode_nccl_comm_destroy", "bode_ekld_argmax_nccl", "bode_argmax_combine",
-    "bode_ekld_prepare_jitter_dev",
+    "bode_ekld_prepare_jitter_dev", "bode_ekld_prepare_quad_rm_dev",
 )
 
 
@@ -85,6 +85,10 @@ def load():
     lib.bode_ekld_prepare_quad_dev.argtypes = [c_dp, c_dp, c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                ctypes.c_double, ctypes.c_double, c_dp, c_dp, ctypes.c_int, c_dp,
                                                ctypes.c_size_t, c_dp, c_dp, c_dp]
+    lib.bode_ekld_prepare_quad_rm_dev.restype = ctypes.c_int
+    lib.bode_ekld_prepare_quad_rm_dev.argtypes = [c_dp, c_dp, c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                  ctypes.c_double, ctypes.c_double, c_dp, c_dp, ctypes.c_int, c_dp, c_dp,
+                                                  ctypes.c_size_t, c_dp, c_dp, c_dp]
     lib.bode_ekld_score_quad_dev.restype = ctypes.c_int
     lib.bode_ekld_score_quad_dev.argtypes = [c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_dp, ctypes.c_int, c_dp,
                                              ctypes.c_int64, ctypes.c_int64, ctypes.c_int, c_dp, c_dp, ctypes.c_int,

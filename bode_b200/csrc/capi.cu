@@ -202,7 +202,7 @@ static bool rec_better(double av, int64_t ai, double bv, int64_t bi) {
 
 extern "C" {
 
-const char* bode_version(void) { return "bode_b200 0.1.0 (sm_100a)"; }
+const char* bode_version(void) { return "bode_b200 0.2.0 (sm_100a)"; }
 
 const char* bode_strerror(int status) {
   switch (status) {
@@ -283,8 +283,8 @@ int bode_quad_rowmean_dev(const double* hyp, int S, int ndim, int d, const doubl
   return BODE_OK;
 }
 
-int bode_ekld_prepare_quad_dev(const double* X, const double* Y, const double* hyp, int n, int d, int S, int ndim,
-                               double nugget_var, double jitter, const double* Xq, const double* wq, int Nq,
+static int prepare_quad_common(const double* X, const double* Y, const double* hyp, int n, int d, int S, int ndim,
+                               double nugget_var, double jitter, const double* Xq, const double* wq, int Nq, const double* rmq_in,
                                void* workspace, size_t workspace_bytes, int* info, void* scratch, void* stream) {
   if (!X || !Y || !hyp || !workspace || !info || !Xq || !scratch || !shape_ok(n, d, S) || Nq < 1) return BODE_ERR_BAD_ARG;
   if (ndim != d + 1 && ndim != d + 2) return BODE_ERR_BAD_ARG;
@@ -299,8 +299,8 @@ int bode_ekld_prepare_quad_dev(const double* X, const double* Y, const double* h
   if (wq) BODE_CUDA(launch_sum_weights(wq, Nq, wsum, st));
   const double* wsp = wq ? wsum : nullptr;
   BODE_CUDA(launch_rowmean(hyp, S, ndim, d, X, n, Xq, wq, Nq, wsp, e, st));      // e_q = mean_q k(X, x_q)
-  BODE_CUDA(launch_rowmean(hyp, S, ndim, d, Xq, Nq, Xq, wq, Nq, wsp, rmq, st));  // mean_q' k(x_q, x_q')
-  BODE_CUDA(launch_weighted_mean(rmq, wq, Nq, wsp, S, s0, st));                  // sigma0_q
+  if (!rmq_in) BODE_CUDA(launch_rowmean(hyp, S, ndim, d, Xq, Nq, Xq, wq, Nq, wsp, rmq, st));  // mean_q' k(x_q, x_q')
+  BODE_CUDA(launch_weighted_mean(rmq_in ? rmq_in : rmq, wq, Nq, wsp, S, s0, st));             // sigma0_q
   PrepArgs a;
   a.X = X; a.Y = Y; a.hyp = hyp; a.n = n; a.d = d; a.S = S; a.ndim = ndim;
   a.nugget_var = nugget_var; a.jitter = jitter; a.jitter_s = nullptr; a.x_smem = 0;
@@ -313,6 +313,22 @@ int bode_ekld_prepare_quad_dev(const double* X, const double* Y, const double* h
   if (workspace_bytes < a.L.total_bytes || (reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return BODE_ERR_WORKSPACE;
   BODE_CUDA(launch_prepare(a, st));
   return BODE_OK;
+}
+
+int bode_ekld_prepare_quad_dev(const double* X, const double* Y, const double* hyp, int n, int d, int S, int ndim,
+                               double nugget_var, double jitter, const double* Xq, const double* wq, int Nq,
+                               void* workspace, size_t workspace_bytes, int* info, void* scratch, void* stream) {
+  return prepare_quad_common(X, Y, hyp, n, d, S, ndim, nugget_var, jitter, Xq, wq, Nq, nullptr, workspace, workspace_bytes, info,
+                             scratch, stream);
+}
+
+int bode_ekld_prepare_quad_rm_dev(const double* X, const double* Y, const double* hyp, int n, int d, int S, int ndim,
+                                  double nugget_var, double jitter, const double* Xq, const double* wq, int Nq,
+                                  const double* rowmean_q, void* workspace, size_t workspace_bytes, int* info, void* scratch,
+                                  void* stream) {
+  if (!rowmean_q) return BODE_ERR_BAD_ARG;
+  return prepare_quad_common(X, Y, hyp, n, d, S, ndim, nugget_var, jitter, Xq, wq, Nq, rowmean_q, workspace, workspace_bytes, info,
+                             scratch, stream);
 }
 
 int bode_gp_loglik_dev(const double* X, const double* Y, const double* hyp, int n, int d, int S, int ndim,

@@ -42,6 +42,7 @@ class EkldEngine:
         self._world = 1
         self._rank = 0
         self._gathered = None
+        self._group = None
         self.jitter_used = None    # per-sample jitter of the last prepare() when jitchol retries were needed
 
     # ---- multi-GPU argmax exchange ------------------------------------------------------------------------
@@ -63,6 +64,7 @@ class EkldEngine:
             comm = ctypes.c_void_p()
             _ext.check(self.lib.bode_nccl_comm_create(ctypes.c_char_p(raw), world, rank, ctypes.byref(comm)))
             self._comm, self._world, self._rank = comm, world, rank
+            self._group = group
             self._gathered = torch.empty(2 * world, dtype=torch.int64, device=self.device)
         return self
 
@@ -147,9 +149,31 @@ class EkldEngine:
                     raise ValueError("one weight per quadrature point")
                 Nq = Xq.shape[0]
                 qs = self._buf("quad_scratch", self.lib.bode_quad_scratch_bytes(n, S, Nq), torch.uint8)
-                _ext.check(self.lib.bode_ekld_prepare_quad_dev(_ptr(Xd), _ptr(Yd), _ptr(H), n, d, S, ndim, float(nugget_var),
-                                                               float(jitter), _ptr(Xq), _ptr(wq), Nq, _ptr(self.ws),
-                                                               self.ws.numel(), _ptr(self.info), _ptr(qs), self._stream()))
+                if self._comm is not None and self._world > 1 and Nq >= 64 * self._world:
+                    # several GPUs (init_nccl): the O(Nq^2 S) row means of the quadrature points are computed in row shards
+                    # and all-gathered (torch.distributed plumbing); sigma0_q is then formed from identical numbers in the
+                    # same order on every rank -- bit-identical to the single-GPU preparation
+                    import torch.distributed as tdist
+                    per = (Nq + self._world - 1) // self._world
+                    lo = min(Nq, self._rank * per)
+                    hi = min(Nq, lo + per)
+                    loc = torch.zeros((S, per), dtype=torch.float64, device=self.device)
+                    if hi > lo:
+                        part = torch.empty((S, hi - lo), dtype=torch.float64, device=self.device)
+                        _ext.check(self.lib.bode_quad_rowmean_dev(_ptr(H), S, ndim, d, _ptr(Xq[lo:hi].contiguous()), hi - lo, _ptr(Xq),
+                                                                  _ptr(wq), Nq, _ptr(part), _ptr(qs), self._stream()))
+                        loc[:, : hi - lo] = part
+                    allr = torch.empty((self._world, S, per), dtype=torch.float64, device=self.device)
+                    tdist.all_gather_into_tensor(allr, loc, group=self._group)
+                    rmq = allr.permute(1, 0, 2).reshape(S, self._world * per)[:, :Nq].contiguous()
+                    _ext.check(self.lib.bode_ekld_prepare_quad_rm_dev(_ptr(Xd), _ptr(Yd), _ptr(H), n, d, S, ndim, float(nugget_var),
+                                                                      float(jitter), _ptr(Xq), _ptr(wq), Nq, _ptr(rmq), _ptr(self.ws),
+                                                                      self.ws.numel(), _ptr(self.info), _ptr(qs), self._stream()))
+                    self._keep_rm = rmq
+                else:
+                    _ext.check(self.lib.bode_ekld_prepare_quad_dev(_ptr(Xd), _ptr(Yd), _ptr(H), n, d, S, ndim, float(nugget_var),
+                                                                   float(jitter), _ptr(Xq), _ptr(wq), Nq, _ptr(self.ws),
+                                                                   self.ws.numel(), _ptr(self.info), _ptr(qs), self._stream()))
                 self.quad = (Xq, wq, Nq)
             self.n, self.d, self.S = n, d, S
             self._ndim = ndim

@@ -138,6 +138,13 @@ int bode_quad_rowmean_dev(const double* hyp, int S, int ndim, int d, const doubl
 int bode_ekld_prepare_quad_dev(const double* X, const double* Y, const double* hyp, int n, int d, int S, int ndim,
                                double nugget_var, double jitter, const double* Xq, const double* wq, int Nq,
                                void* workspace, size_t workspace_bytes, int* info, void* scratch, void* stream);
+/* The same with the S*Nq row means  rowmean_q[s*Nq + q] = mean_q' k_s(x_q, x_q')  supplied by the caller: the O(Nq^2 S) part of
+ * the preparation, which a multi-GPU caller computes in row shards with bode_quad_rowmean_dev (P = its rows of X_quad) and
+ * all-gathers -- every rank then forms sigma0_q from identical numbers in the same order. */
+int bode_ekld_prepare_quad_rm_dev(const double* X, const double* Y, const double* hyp, int n, int d, int S, int ndim,
+                                  double nugget_var, double jitter, const double* Xq, const double* wq, int Nq,
+                                  const double* rowmean_q, void* workspace, size_t workspace_bytes, int* info, void* scratch,
+                                  void* stream);
 /* bode_ekld_score_dev with xi_q(x) in place of xik(x); xi is an S*Nd buffer (returned filled); logk nullable as above;
  * scratch >= 256 + bode_ekld_score_scratch_bytes(Nd, logk ? S : 2 * S). */
 int bode_ekld_score_quad_dev(const void* workspace, int n, int d, int S, const double* hyp, int ndim,

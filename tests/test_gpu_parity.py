@@ -382,7 +382,13 @@ def _nccl_worker(rank, world, port, payload, q):
         eng.prepare(X, Y, hyp, 1e-6)
         res = bdist.sharded_score(eng, Xd, group=tdist.group.WORLD)
         empty = bdist.sharded_score(eng, Xd[:1], group=tdist.group.WORLD)   # rank 1 has no candidates
-        q.put((rank, res["idx_best"], res["best"], res["score"].tolist(), res["var"].tolist(), empty["idx_best"]))
+        # quadrature mode: the O(Nq^2 S) row means of the quadrature points are computed in row shards and all-gathered
+        Xq = np.random.default_rng(3).random((777, X.shape[1]))
+        eng.prepare(X, Y, hyp, 1e-6, quad=(Xq, None))
+        mq = eng.mu_sigma()
+        rq = bdist.sharded_score(eng, Xd[:500], group=tdist.group.WORLD)
+        q.put((rank, res["idx_best"], res["best"], res["score"].tolist(), res["var"].tolist(), empty["idx_best"],
+               list(mq), rq["score"].tolist(), rq["idx_best"]))
         eng.close_nccl()
     finally:
         tdist.destroy_process_group()
@@ -407,11 +413,21 @@ def test_two_ranks_over_nccl_match_single_rank_bitwise(engine):
     out = sorted(q.get(timeout=300) for _ in range(2))
     [p.join(timeout=120) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
-    for rank, idx, best, score, var, idx_empty in out:
-        assert idx == int(one["best_idx"].item()) and best == float(one["best"].item())
-        np.testing.assert_array_equal(np.array(score), one["score"].cpu().numpy())
-        np.testing.assert_array_equal(np.array(var), one["var"].cpu().numpy())
+    one_score, one_var = one["score"].cpu().numpy(), one["var"].cpu().numpy()
+    one_best = (int(one["best_idx"].item()), float(one["best"].item()))
+    Xq = np.random.default_rng(3).random((777, X.shape[1]))
+    engine.prepare(X, Y, hyp, 1e-6, quad=(Xq, None))
+    mq1 = engine.mu_sigma()
+    rq1 = engine.score(Xd[:500])
+    for rank, idx, best, score, var, idx_empty, mq, sq, iq in out:
+        assert (idx, best) == one_best
+        np.testing.assert_array_equal(np.array(score), one_score)
+        np.testing.assert_array_equal(np.array(var), one_var)
         assert idx_empty == 0
+        assert tuple(mq) == tuple(mq1)                                    # sharded quadrature preparation: same bits
+        np.testing.assert_array_equal(np.array(sq), rq1["score"].cpu().numpy())
+        assert iq == int(rq1["best_idx"].item())
+    engine.prepare(X, Y, hyp, 1e-6)
 
 
 @pytest.mark.parametrize("n,d", [(1, 2), (7, 3), (8, 1), (9, 4), (60, 6), (200, 8), (217, 10), (224, 16)])

@@ -347,6 +347,10 @@ class StepGraph(object):
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self.out = body()
+            # the graph replays against the engine buffers that existed at capture time: keep them alive even if the engine
+            # later outgrows them (a larger design would otherwise hand their memory back to the allocator)
+            self._hold = (dict(engine._scratch), engine.ws, engine.info, engine._gathered, getattr(engine, "_keep", None),
+                          getattr(engine, "_keep_x", None), X, Y, hyp, X_design)
 
     def launch(self):
         """Enqueue the step (no host synchronisation); results land in ``self.out`` / the engine's gather buffer."""

@@ -282,12 +282,12 @@ class KLSampler(object):
         ``make_mcmc_model`` (``_sampler.py:453``), and what still fails raises instead of poisoning the scores with NaN
         (a NaN would win the argmax, ``np.argmax`` semantics)."""
         info = self.engine.prepare(X, Y, model[0], self.nugget ** 2, quad=self._quad(), jitchol_retries=5)
-        bad = np.nonzero(np.asarray(info.cpu() if hasattr(info, "cpu") else info) != 0)[0]
+        codes = np.asarray(info.cpu() if hasattr(info, "cpu") else info)
+        bad = np.nonzero(codes != 0)[0]
         if bad.size:
             from ._ext import BodeError
-            codes = np.asarray(info.cpu() if hasattr(info, "cpu") else info)[bad]
-            raise BodeError(-5, "hyper-samples %s: %s" % (bad.tolist()[:8], "invalid hyper-parameters (info = -1)" if (codes < 0).any()
-                                                          else "not positive definite, even with jitter (info = %s)" % codes.tolist()[:8]))
+            raise BodeError(-5, "hyper-samples %s: %s" % (bad.tolist()[:8], "invalid hyper-parameters (info = -1)" if (codes[bad] < 0).any()
+                                                          else "not positive definite, even with jitter (info = %s)" % codes[bad].tolist()[:8]))
         if getattr(self.engine, "jitter_used", None) is not None:
             print('>... Cholesky retried with added jitter for %d hyper-sample(s) (GPy jitchol semantics)'
                   % int((self.engine.jitter_used > 1e-8).sum()))

@@ -427,12 +427,13 @@ size_t prepare_smem_bytes(const Layout& L) {
 }
 
 size_t prepare_tiles_smem_bytes(const Layout& L);                          // prepare_tiles.cu
+size_t smem_optin_bytes();                                                 // prepare_tiles.cu
 cudaError_t launch_prepare_tiles(const PrepArgs& a, cudaStream_t st);      // prepare_tiles.cu
 
 cudaError_t launch_prepare(const PrepArgs& a, cudaStream_t st) {
   // n <= 224: the bordered triangle fits in shared memory and the factorisation runs on the FP64 tensor pipe
   // (prepare_tiles.cu); larger n (or BODE_PREP_VARIANT=0): the global-memory kernel below
-  if (tuning().prep_variant != 0 && a.L.nrt <= 28 && prepare_tiles_smem_bytes(a.L) + 64 <= 232448)
+  if (tuning().prep_variant != 0 && a.L.nrt <= 28 && prepare_tiles_smem_bytes(a.L) + 64 <= smem_optin_bytes())
     return launch_prepare_tiles(a, st);
   const size_t smem = prepare_smem_bytes(a.L);
   static thread_local int attr_dev = -1;

@@ -16,7 +16,7 @@ struct PrepArgs {
   // quadrature mode (nullable): kernel mean embedding of the observations and double integral supplied by k_rowmean
   const double* e_ovr;       // S*n   replaces xik(X)
   const double* sigma0_ovr;  // S     replaces bk
-  int x_smem;                // (set by the tile kernel's launcher) observations staged in shared memory
+  int x_smem;                // (set by the tile kernel's launcher) the scaled observation tiles are staged in shared memory
   int loglik_only;           // 1: stop after the factorisation scalars (host MCMC likelihoods): no w, no L^-1, no tiling
 };
 }  // namespace bode

@@ -516,12 +516,27 @@ size_t prepare_tiles_smem_bytes(const Layout& L) {
   const size_t coef = 8 * 64;
   return sizeof(double) * (fact > coef ? fact : coef);
 }
+// opt-in shared memory per CTA of the current device (232 448 B on B200), queried once per thread and device
+size_t smem_optin_bytes() {
+  static thread_local int dev_cached = -1;
+  static thread_local size_t bytes = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (dev != dev_cached) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 0;
+    bytes = (size_t)v;
+    dev_cached = dev;
+  }
+  return bytes;
+}
+
 static size_t prepare_tiles_xs_bytes(const Layout& L) { return sizeof(double) * (size_t)L.npad * 4 * L.dk; }
 
 cudaError_t launch_prepare_tiles(const PrepArgs& a_in, cudaStream_t st) {
   PrepArgs a = a_in;
   size_t smem = prepare_tiles_smem_bytes(a.L);
-  a.x_smem = smem + prepare_tiles_xs_bytes(a.L) + 64 <= 232448 ? 1 : 0;  // stage the observations when there is room
+  a.x_smem = smem + prepare_tiles_xs_bytes(a.L) + 64 <= smem_optin_bytes() ? 1 : 0;  // stage the scaled tiles when there is room
   if (a.x_smem) smem += prepare_tiles_xs_bytes(a.L);
   static thread_local int attr_dev = -1;
   static thread_local size_t attr_smem = 0;

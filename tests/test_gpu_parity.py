@@ -485,6 +485,30 @@ def test_step_graph_replays_match_plain_calls(engine):
     engine.prepare(X, Y, hyp, 1e-6)
 
 
+def test_tile_prepare_kernel_random_shapes(engine):
+    """Randomised sweep over (n, d, S) for the shared-memory tile prepare kernel (every n mod 8, one to 28 row tiles): the
+    per-sample by-products against the oracle (triangular route, well-conditioned lengthscales), the scores against the
+    vectorised oracle on a few candidates.  compute-sanitizer is closed on this pool, so shape coverage stands in for it."""
+    rng = np.random.default_rng(2026)
+    shapes = [(int(n), int(rng.integers(1, 17)), int(rng.integers(1, 6))) for n in
+              list(rng.integers(1, 225, size=18)) + [8, 16, 17, 223, 224]]
+    for n, d, S in shapes:
+        X, Y, Xd, hyp = cases.make_problem(d, n, S, 40, seed=7000 + n + 13 * d, ell_lo=0.35, ell_hi=0.9)
+        info = engine.prepare(X, Y, hyp, 1e-6)
+        assert int(info.abs().max()) == 0, (n, d, S)
+        terms = engine.sample_terms().cpu().numpy()
+        ref = orc.score(X, Y, Xd, hyp)
+        t = truth.ekld_truth(X, Y, Xd, hyp)
+        # scalars against the 80-bit evaluation (many points in few dimensions are ill-conditioned: the oracle's explicit
+        # inverse is then the less accurate side); sigma_1 = sigma_0 - a.a cancels
+        np.testing.assert_allclose(terms[:, 7], t["loglik"], rtol=1e-9, atol=1e-7, err_msg=str((n, d, S)))
+        np.testing.assert_allclose(terms[:, 4], t["mu_1"], rtol=1e-7, atol=1e-10, err_msg=str((n, d, S)))
+        np.testing.assert_allclose(terms[:, 3], t["sigma_1"], rtol=1e-5, atol=1e-13, err_msg=str((n, d, S)))
+        r = engine.score(Xd)
+        assert_t2(np.exp(r["logk"].cpu().numpy()), ref["kld"], t["kld"], what=str((n, d, S)))
+        assert_argmax(int(r["best_idx"].item()), np.log(t["kld"]).mean(0), tol=1e-7)
+
+
 def test_invalid_hyperparameters_are_rejected(ext):
     X, Y, Xd, hyp = cases.make_problem(2, 10, 3, 20, seed=2)
     hyp[1, 1] = -0.3   # negative lengthscale

@@ -4,7 +4,7 @@
 // (get_params_2 :391-402, predict / kern.K inside GPy, xik _core.py:86-92), and the log / mean / var / argmax of
 // mcmc_kld + optimize (:492, :659).  Per (candidate x, hyper-sample s):
 //     k   = K_ARD-RBF(X, x; theta_s)            (K2, phase A: GEMM-form distance on the tensor pipe + exp2, never leaves smem)
-//     xi  = xik(x)                               (k_xi: even Chebyshev series of the d factors, erf fallback)
+//     xi  = xik(x)                               (k_ekld_reduce: even Chebyshev series of the d factors, erf fallback)
 //     t   = L_s^-1 k ; sigma_x = ss - t.t        (K3, phase B: FP64 tensor-core DMMA.8x8x4 against the tiled L^-1)
 //     v   = xi - w_s.k                           (K3, folded into phase A)
 //     EKLD = log(sqrt(s1)/sqrt(s2)) + s2/(2 s1) + (v^2/s1/(sigma_x+noise))*0.5 - 0.5 ; logk = log(EKLD)   (K4)

@@ -125,7 +125,7 @@ def test_combine_argmax_semantics():
 
 
 def test_xik_factor_chebyshev_series_method():
-    """The numerical method behind k_xik_coef / k_ekld, restated in NumPy: the xik factor
+    """The numerical method behind xik_coef_block / k_ekld_reduce, restated in NumPy: the xik factor
     F(x) = sqrt(pi/2) ell (erf((1-x)c) + erf(xc)) is even about x = 1/2, so it is a series in T_j(2(2x-1)^2 - 1) computed
     from 64 Gauss-Chebyshev nodes and cut at its rounding floor; the cut series reproduces F to ~1e-15 with a handful of
     terms, and very short lengthscales are detected as not converged (erf path)."""

@@ -232,17 +232,20 @@ __device__ __forceinline__ void phase_a(const double* __restrict__ aux, const do
   for (int i = 0; i < DK; i++) yb[i] = (xt[(4 * i + q) * C + 8 * ctile + r] - 0.5) * cks[4 * i + q];
   // -|y|^2 of the two candidates this thread's accumulators belong to (tile columns 2q, 2q + 1), fixed order over k
   // (the padded dimensions k >= d have cks = 0 and add exact zeros)
-  double nyn[2] = {0.0, 0.0};
+  // (even and odd k in separate chains, added at the end: half the dependent latency of this once-per-sample setup)
+  double nyn[2], nye[2] = {0.0, 0.0}, nyo[2] = {0.0, 0.0};
 #pragma unroll
-  for (int k = 0; k < 4 * DK; k++) {
-    const double c2 = cks[k];
+  for (int k = 0; k < 4 * DK; k += 2) {
+    const double c2 = cks[k], c3 = cks[k + 1];
     const double t0 = (xt[k * C + 8 * ctile + 2 * q] - 0.5) * c2, t1 = (xt[k * C + 8 * ctile + 2 * q + 1] - 0.5) * c2;
-
-    nyn[0] = fma(-t0, t0, nyn[0]);
-    nyn[1] = fma(-t1, t1, nyn[1]);
+    const double t2 = (xt[(k + 1) * C + 8 * ctile + 2 * q] - 0.5) * c3, t3 = (xt[(k + 1) * C + 8 * ctile + 2 * q + 1] - 0.5) * c3;
+    nye[0] = fma(-t0, t0, nye[0]);
+    nye[1] = fma(-t1, t1, nye[1]);
+    nyo[0] = fma(-t2, t2, nyo[0]);
+    nyo[1] = fma(-t3, t3, nyo[1]);
   }
-  nyn[0] *= 0.25;
-  nyn[1] *= 0.25;
+  nyn[0] = (nye[0] + nyo[0]) * 0.25;
+  nyn[1] = (nye[1] + nyo[1]) * 0.25;
   TSA(0);
   double wk[2] = {0.0, 0.0};
   const double2* nw = reinterpret_cast<const double2*>(nwp);
@@ -565,7 +568,7 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
     };
     auto leave = [&]() {  // done with chunk q
       __syncwarp();
-      if (elect_one()) mbar_arrive(empty0 + 8 * st);
+      if (lane == 0) mbar_arrive(empty0 + 8 * st);
       if (++st == stages) { st = 0; ph ^= 1; }
       ++it;
     };

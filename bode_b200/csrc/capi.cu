@@ -409,6 +409,8 @@ static int score_common(const void* workspace, int n, int d, int S, const double
   a.wk = wkp;
   a.done_counter = done_counter;
   a.sc = P.sc; a.ntiles = P.ntiles; a.form = form; a.mode = mode;
+  a.n_main = P.n_main; a.n_tail = P.n_tail;
+  memcpy(a.tail_s0, P.tail_s0, sizeof(a.tail_s0));
   a.debug_skip = tuning().debug_skip;
   a.stagger = tuning().stagger;
   a.stages = P.stages; a.chunk_max = P.chunk_max; a.nchunks = P.nchunks; a.u_global = P.u_global;
@@ -679,6 +681,9 @@ int bode_ekld_plan_describe(int n, int d, int S, int64_t Nd, int sm_count, size_
     for (int t = 0; t < P.rt && (size_t)w < cap; t++) w += snprintf(out + w, cap - w, "%s%d", t ? ", " : "", (int)P.tile_id[g * kMaxRT + t]);
     if ((size_t)w < cap) w += snprintf(out + w, cap - w, "]");
   }
+  if (w > 0 && (size_t)w < cap) w += snprintf(out + w, cap - w, "], \"main_chunks\": %d, \"tail_s0\": [", P.n_main);
+  for (int j = 0; j <= P.n_tail && P.n_tail > 0 && w > 0 && (size_t)w < cap; j++)
+    w += snprintf(out + w, cap - w, "%s%d", j ? ", " : "", (int)P.tail_s0[j]);
   if (w > 0 && (size_t)w < cap) w += snprintf(out + w, cap - w, "]}");
   return (w > 0 && (size_t)w < cap) ? BODE_OK : BODE_ERR_BAD_ARG;
 }

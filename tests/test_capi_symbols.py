@@ -90,16 +90,41 @@ def test_launch_plans_are_consistent(built_lib, n):
     assert p["smem_bytes"] <= 232448 and p["stages"] >= 2 and p["threads"] in (256, 512)
     assert p["candidates_per_cta"] == p["col_groups"] * p["col_tiles_per_warp"] * 8
     assert p["tiles"] == -(-Nd // p["candidates_per_cta"])
-    assert p["items"] == p["tiles"] * -(-S // p["samples_per_item"])
+    _check_sample_schedule(p, S)
     assert p["items"] >= 148
+
+
+def _check_sample_schedule(p, S):
+    """Work items = tiles x hyper-sample chunks; the chunks (equal ones, then the tapered tail) cover 0..S once, largest first."""
+    sc, nm, tail = p["samples_per_item"], p["main_chunks"], p["tail_s0"]
+    chunks = [(i * sc, min(S, (i + 1) * sc)) for i in range(nm)] + list(zip(tail, tail[1:]))
+    assert p["items"] == p["tiles"] * len(chunks)
+    assert chunks[0][0] == 0 and chunks[-1][1] == S and all(a[1] == b[0] for a, b in zip(chunks, chunks[1:]))
+    sizes = [b - a for a, b in chunks]
+    assert all(x >= 1 for x in sizes) and sizes == sorted(sizes, reverse=True)
+
+
+@pytest.mark.parametrize("S,Nd", [(64, 100000), (64, 12500), (60, 100000), (128, 1000000), (1, 100000), (2, 20000), (33, 9472), (64, 9471)])
+def test_sample_chunks_taper_when_there_are_more_tiles_than_sms(built_lib, S, Nd):
+    from bode_b200 import _ext
+    p = _ext.plan_describe(200, 8, S, Nd)
+    _check_sample_schedule(p, S)
+    if p["tiles"] >= 148 and S > 1:   # halving chunks: the last wave of CTAs is made of one-sample items
+        tail = p["tail_s0"]
+        sizes = [b - a for a, b in zip(tail, tail[1:])]
+        assert p["main_chunks"] == 0 and sizes[0] == (S + 1) // 2 and sizes[-1] == 1
+    else:
+        assert p["tail_s0"] == []
 
 
 def test_launch_plan_small_problem_uses_all_sms(built_lib):
     from bode_b200 import _ext
     p = _ext.plan_describe(200, 8, 64, 1000)      # 16 tiles only: split the hyper-samples to fill the GPU
     assert p["items"] >= 148 and p["samples_per_item"] < 64
+    _check_sample_schedule(p, 64)
     q = _ext.plan_describe(200, 8, 2, 100)        # tiny: cannot fill, must still be valid
     assert q["items"] == 2 * 2 and q["samples_per_item"] == 1
+    _check_sample_schedule(q, 2)
     lib = _ext.load()
     import ctypes
     buf = ctypes.create_string_buffer(4096)

@@ -328,10 +328,25 @@ class StepGraph(object):
         self.eng = engine
         dev = engine.device
 
+        copy_stream = torch.cuda.Stream(device=dev)
+        host_design = isinstance(X_design, torch.Tensor) and X_design.device.type == "cpu"
+
         def body():
             to = lambda t: t.to(dev, non_blocking=True) if isinstance(t, torch.Tensor) else t
-            engine.prepare(to(X), to(Y), to(hyp), nugget_var, jitter, quad=quad)
-            r = engine.score(to(X_design), idx_offset=idx_offset, form=form, want_var=want_var, want_logk=want_logk)
+            cur = torch.cuda.current_stream()
+            xd = X_design
+            dX, dY, dH = to(X), to(Y), to(hyp)
+            if host_design:  # the design block's host->device copy does not depend on the factorisations: a forked branch
+                copy_stream.wait_stream(cur)  # of the graph (behind the small copies: one DMA queue), joined before scoring
+                with torch.cuda.stream(copy_stream):
+                    xd = X_design.to(dev, non_blocking=True)
+            engine.prepare(dX, dY, dH, nugget_var, jitter, quad=quad)
+            if host_design:
+                cur.wait_stream(copy_stream)  # (xd is held by this object for the life of the graph: no record_stream needed)
+            else:
+                xd = to(xd)
+            self._xd = xd
+            r = engine.score(xd, idx_offset=idx_offset, form=form, want_var=want_var, want_logk=want_logk)
             if engine._comm is not None:
                 _ext.check(engine.lib.bode_ekld_argmax_nccl(engine._comm, _ptr(r["rec"]), _ptr(engine._gathered), engine._stream()))
             return r
@@ -350,7 +365,7 @@ class StepGraph(object):
             # the graph replays against the engine buffers that existed at capture time: keep them alive even if the engine
             # later outgrows them (a larger design would otherwise hand their memory back to the allocator)
             self._hold = (dict(engine._scratch), engine.ws, engine.info, engine._gathered, getattr(engine, "_keep", None),
-                          getattr(engine, "_keep_x", None), X, Y, hyp, X_design)
+                          getattr(engine, "_keep_x", None), X, Y, hyp, X_design, self._xd, copy_stream)
 
     def launch(self):
         """Enqueue the step (no host synchronisation); results land in ``self.out`` / the engine's gather buffer."""

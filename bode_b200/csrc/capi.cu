@@ -108,6 +108,8 @@ struct bode_ctx {
   std::mutex mu;
   int device = -1;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // the design block's host->device copy overlaps the factorisations
+  cudaEvent_t copied = nullptr, inputs_in = nullptr;
   struct Buf {
     void* p = nullptr;
     size_t cap = 0;
@@ -141,6 +143,9 @@ static int ctx_bind(bode_ctx* c) {
   if (c->device < 0) {
     c->device = dev;
     BODE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    BODE_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    BODE_CUDA(cudaEventCreateWithFlags(&c->copied, cudaEventDisableTiming));
+    BODE_CUDA(cudaEventCreateWithFlags(&c->inputs_in, cudaEventDisableTiming));
   } else if (c->device != dev) {
     return BODE_ERR_BAD_ARG;  // a context belongs to the device it was first used on
   }
@@ -492,6 +497,9 @@ int bode_ctx_destroy(bode_ctx* c) {
   for (auto& buf : c->b)
     if (buf.p) cudaFree(buf.p);
   if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->copied) cudaEventDestroy(c->copied);
+  if (c->inputs_in) cudaEventDestroy(c->inputs_in);
   delete c;
   return BODE_OK;
 }
@@ -530,10 +538,17 @@ int bode_ekld_score_host_ctx(bode_ctx* c, const double* X, const double* Y, cons
   BODE_CUDA(cudaMemcpyAsync(c->b[B::kX].p, X, sizeof(double) * n * d, cudaMemcpyHostToDevice, st));
   BODE_CUDA(cudaMemcpyAsync(c->b[B::kY].p, Y, sizeof(double) * n, cudaMemcpyHostToDevice, st));
   BODE_CUDA(cudaMemcpyAsync(c->b[B::kH].p, hyp, sizeof(double) * S * ndim, cudaMemcpyHostToDevice, st));
-  BODE_CUDA(cudaMemcpyAsync(c->b[B::kXd].p, X_design, sizeof(double) * Nd * d, cudaMemcpyHostToDevice, st));
+  BODE_CUDA(cudaEventRecord(c->inputs_in, st));
   rc = bode_ekld_prepare_dev(c->as<double>(B::kX), c->as<double>(B::kY), c->as<double>(B::kH), n, d, S, ndim, nugget_var, jitter,
                              c->b[B::kWs].p, wsb, c->as<int>(B::kInfo), st);
   if (rc != BODE_OK) return rc;
+  // the design block goes up on a second stream while the factorisations run (behind the small copies: the host->device
+  // DMA queue is served in order; after the launch: a copy from pageable memory blocks the host).  The previous call's
+  // scoring kernel, the last reader of the buffer, has finished: every call ends synchronised.
+  BODE_CUDA(cudaStreamWaitEvent(c->copy_stream, c->inputs_in, 0));
+  BODE_CUDA(cudaMemcpyAsync(c->b[B::kXd].p, X_design, sizeof(double) * Nd * d, cudaMemcpyHostToDevice, c->copy_stream));
+  BODE_CUDA(cudaEventRecord(c->copied, c->copy_stream));
+  BODE_CUDA(cudaStreamWaitEvent(st, c->copied, 0));
   double* dbest = c->as<double>(B::kBest);
   int64_t* dbest_idx = reinterpret_cast<int64_t*>(dbest + 1);
   rc = bode_ekld_score_dev(c->b[B::kWs].p, n, d, S, c->as<double>(B::kXd), Nd, 0, form, c->as<double>(B::kPlane),

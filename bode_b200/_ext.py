@@ -20,7 +20,7 @@ BODE_MAX_D = 16
 
 EXPORTS = (
     "bode_version", "bode_strerror", "bode_last_cuda_error", "bode_ekld_workspace_bytes", "bode_ekld_prepare_dev",
-    "bode_ekld_sample_terms_dev", "bode_ekld_mu_sigma_dev", "bode_ekld_score_scratch_bytes", "bode_ekld_score_dev",
+    "bode_ekld_sample_terms_dev", "bode_ekld_mu_sigma_dev", "bode_ekld_score_scratch_bytes", "bode_ekld_score_dev", "bode_ekld_rescore_dev",
     "bode_ekld_score_dev_timed", "bode_ekld_score_dev_events", "bode_us_variance_dev", "bode_quad_scratch_bytes", "bode_quad_rowmean_dev",
     "bode_ekld_prepare_quad_dev", "bode_ekld_score_quad_dev", "bode_ekld_score_host", "bode_gp_loglik_host", "bode_gp_loglik_dev", "bode_ekld_plan_describe", "bode_fp64_peak",
     "bode_tuning_reload", "bode_ctx_create", "bode_ctx_destroy", "bode_ctx_alloc_count", "bode_ekld_score_host_ctx", "bode_gp_loglik_host_ctx",
@@ -72,6 +72,9 @@ def load():
     lib.bode_ekld_score_dev.restype = ctypes.c_int
     lib.bode_ekld_score_dev.argtypes = [c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_dp, ctypes.c_int64,
                                         ctypes.c_int64, ctypes.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]
+    lib.bode_ekld_rescore_dev.restype = ctypes.c_int
+    lib.bode_ekld_rescore_dev.argtypes = [c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_dp, ctypes.c_int64,
+                                          ctypes.c_int64, ctypes.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]
     lib.bode_ekld_score_dev_timed.restype = ctypes.c_int
     lib.bode_ekld_score_dev_timed.argtypes = list(lib.bode_ekld_score_dev.argtypes) + [c_dp]
     lib.bode_ekld_score_dev_events.restype = ctypes.c_int

@@ -319,17 +319,26 @@ class KLSampler(object):
         self._prepare(model, self.X, self.Y)
         mu, sigma = self.engine.mu_sigma()
         group = self.process_group if self._sharded else None
-        res = _dist.sharded_score(self.engine, X_design, form=self.ekld_form, group=group)
-        res.update(mu=mu, sigma=sigma)
         check = self.ekld_form_check
         if check is None:
             check = np.asarray(X_design).shape[0] * np.asarray(model[0]).shape[0] <= 2e6
-        if self.ekld_form == 1 and check:
-            lit = _dist.sharded_score(self.engine, X_design, form=0, group=group, want_var=False)
-            bad = int(np.sum(~np.isfinite(lit["score"])))
-            if bad or lit["idx_best"] != res["idx_best"]:
-                print('>... WARNING: ekld_form=1 (log1p form) selects design %d; the reference expression (_sampler.py:480) selects %d'
-                      ' (%d candidate scores are NaN/-inf under its 2e-16 noise floor)' % (res["idx_best"], lit["idx_best"], bad))
+        check = bool(check) and self.ekld_form == 1
+        # The literal form first, leaving its sigma_x / w.k planes in place; the log1p form is then the reduction kernel alone
+        # on the same planes (engine.rescore): the check costs a few percent of a scoring call, not a second one.
+        cheap = check and self.ekld_mode == 'closed' and hasattr(self.engine, "rescore")
+        lit = None
+        if cheap:
+            lit = _dist.sharded_score(self.engine, X_design, form=0, group=group, want_var=False, want_scores=False, keep_planes=True)
+        res = _dist.sharded_score(self.engine, X_design, form=self.ekld_form, group=group, rescore=cheap)
+        res.update(mu=mu, sigma=sigma)
+        if check:
+            if lit is None:
+                lit = _dist.sharded_score(self.engine, X_design, form=0, group=group, want_var=False, want_scores=False)
+            nan_wins = not np.isfinite(lit["best"])  # np.argmax semantics: a NaN score is the maximum
+            if nan_wins or lit["idx_best"] != res["idx_best"]:
+                print('>... WARNING: ekld_form=1 (log1p form) selects design %d; the reference expression (_sampler.py:480) selects %d%s'
+                      % (res["idx_best"], lit["idx_best"],
+                         ' (a NaN score: the expression is below its 2e-16 noise floor there)' if nan_wins else ''))
             res["idx_best_literal"] = lit["idx_best"]
         return res
 

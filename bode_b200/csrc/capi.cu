@@ -387,7 +387,7 @@ size_t bode_ekld_score_scratch_bytes(int64_t Nd, int S) {
 static int score_common(const void* workspace, int n, int d, int S, const double* Xd, int64_t Nd, int64_t idx_offset,
                         int form, int mode, const double* xi_ovr, double* logk, double* score, double* var, double* best,
                         int64_t* best_idx, void* scratch, void* stream, float* kernel_ms, void* ev_start = nullptr,
-                        void* ev_stop = nullptr) {
+                        void* ev_stop = nullptr, bool reuse_planes = false) {
   if (!workspace || !Xd || !score || !best || !best_idx || !scratch || !shape_ok(n, d, S) || Nd < 1)
     return BODE_ERR_BAD_ARG;
   if (form != BODE_FORM_REFERENCE && form != BODE_FORM_LOG1P) return BODE_ERR_BAD_ARG;
@@ -428,7 +428,7 @@ static int score_common(const void* workspace, int n, int d, int S, const double
     BODE_CUDA(cudaEventRecord(ev0, st));
   }
   if (ev_start) BODE_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_start), st));
-  BODE_CUDA(launch_score(a, P, st));
+  if (!reuse_planes) BODE_CUDA(launch_score(a, P, st));
   if (ev_stop) BODE_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_stop), st));
   if (kernel_ms) BODE_CUDA(cudaEventRecord(ev1, st));
   if (mode == kModeEkld)
@@ -450,6 +450,13 @@ int bode_ekld_score_dev(const void* workspace, int n, int d, int S, const double
                         int64_t* best_idx, void* scratch, void* stream) {
   return score_common(workspace, n, d, S, X_design, Nd, idx_offset, form, kModeEkld, nullptr, logk, score, var, best, best_idx,
                       scratch, stream, nullptr);
+}
+
+int bode_ekld_rescore_dev(const void* workspace, int n, int d, int S, const double* X_design, int64_t Nd,
+                          int64_t idx_offset, int form, double* score, double* var, double* best, int64_t* best_idx,
+                          void* scratch, void* stream) {
+  return score_common(workspace, n, d, S, X_design, Nd, idx_offset, form, kModeEkld, nullptr, nullptr, score, var, best, best_idx,
+                      scratch, stream, nullptr, nullptr, nullptr, true);
 }
 
 int bode_ekld_score_dev_timed(const void* workspace, int n, int d, int S, const double* X_design, int64_t Nd,

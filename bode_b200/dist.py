@@ -77,26 +77,40 @@ def gather_rows(local, n_total, group=None):
     return torch.cat(out)[:n_total]
 
 
-def sharded_score(engine, X_design, form=0, group=None, want_scores=True, want_var=True):
+def sharded_score(engine, X_design, form=0, group=None, want_scores=True, want_var=True, keep_planes=False, rescore=False):
     """Score ``X_design`` (host array, identical on every rank) on this rank's shard and combine across ranks.
 
     Shards only when a process group is passed explicitly (``torch.distributed.group.WORLD`` for the default one): a
     caller that merely runs inside an initialised job is not silently split.  Returns dict(score (Nd,) NumPy or None,
-    var, idx_best (global), best).
+    var, idx_best (global), best).  ``keep_planes`` (with ``want_var=False``) leaves the engine able to ``rescore``;
+    ``rescore=True`` evaluates ``form`` from the planes of such a preceding call on the same design (reduction kernel only).
     """
+
+    def run(xd, off):
+        if rescore:
+            return engine.rescore(idx_offset=off, form=form, want_var=want_var)
+        if keep_planes:
+            return engine.score(xd, idx_offset=off, form=form, want_var=False, want_logk=False)
+        return engine.score(xd, idx_offset=off, form=form, want_var=want_var)
+
     import torch.distributed as dist
     Xd = np.ascontiguousarray(X_design, dtype=np.float64)
     Nd = Xd.shape[0]
     if group is None or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        r = engine.score(Xd, form=form, want_var=want_var)
-        return dict(score=r["score"].cpu().numpy(), var=r["var"].cpu().numpy() if want_var else None,
-                    idx_best=int(r["best_idx"].item()), best=float(r["best"].item()))
+        r = run(Xd, 0)
+        if r.get("rec") is not None:
+            rec = r["rec"].cpu()  # (best, best_idx) in one device->host read
+            best, idx = float(rec[:1].view(torch.float64).item()), int(rec[1].item())
+        else:
+            best, idx = float(r["best"].item()), int(r["best_idx"].item())
+        return dict(score=r["score"].cpu().numpy() if want_scores else None,
+                    var=r["var"].cpu().numpy() if (want_scores and r.get("var") is not None) else None, idx_best=idx, best=best)
     ws, rank = dist.get_world_size(group), dist.get_rank(group)
     lo, hi = shard_bounds(Nd, ws, rank)
     dev = engine.device
     use_capi = getattr(engine, "_comm", None) is not None  # EkldEngine.init_nccl(): C-ABI exchange on the compute stream
     if hi > lo:
-        r = engine.score(Xd[lo:hi], idx_offset=lo, form=form, want_var=want_var)
+        r = run(Xd[lo:hi], lo)
         bv, bi, sc, vr, rec = r["best"], r["best_idx"], r["score"], r["var"], r.get("rec")
     else:
         bv = torch.full((1,), float("-inf"), dtype=torch.float64, device=dev)

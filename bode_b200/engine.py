@@ -178,6 +178,7 @@ class EkldEngine:
             self.n, self.d, self.S = n, d, S
             self._ndim = ndim
             self._prepared = True
+            self._planes_ok = False
             self._keep = (Xd, Yd, H)  # keep inputs alive until the stream has consumed them
             self.jitter_used = None
             if jitchol_retries > 0 and quad is None:
@@ -289,7 +290,28 @@ class EkldEngine:
             else:
                 _ext.check(self.lib.bode_ekld_score_dev(*args))
             self._keep_x = Xd
+            # the sigma_x / w.k planes stay intact in scratch only when neither logk nor var was asked for: rescore() needs that
+            self._planes_ok = (not want_var) and (not want_logk)
         return dict(score=score, var=var, logk=logk, best=best, best_idx=best_idx, rec=rec)
+
+    def rescore(self, idx_offset=0, form=_ext.BODE_FORM_REFERENCE, want_var=True):
+        """The other EKLD form for the design of the previous ``score(..., want_var=False, want_logk=False)`` call: only the
+        reduction kernel runs again, on the planes that call left in scratch (``bode_ekld_rescore_dev``).  Same return
+        value as ``score`` without ``logk``."""
+        if not getattr(self, "_planes_ok", False) or self.quad is not None:
+            raise RuntimeError("rescore() must follow score(want_var=False, want_logk=False) on the same prepared state")
+        with torch.cuda.device(self.device):
+            Xd = self._keep_x
+            Nd = Xd.shape[0]
+            score = torch.empty(Nd, dtype=torch.float64, device=self.device)
+            var = torch.empty(Nd, dtype=torch.float64, device=self.device) if want_var else None
+            rec = torch.empty(2, dtype=torch.int64, device=self.device)
+            best, best_idx = rec[:1].view(torch.float64), rec[1:]
+            scr = self._buf("scratch", 256 + self.lib.bode_ekld_score_scratch_bytes(Nd, 2 * self.S), torch.uint8)
+            _ext.check(self.lib.bode_ekld_rescore_dev(_ptr(self.ws), self.n, self.d, self.S, _ptr(Xd), Nd, int(idx_offset), int(form),
+                                                      _ptr(score), _ptr(var), _ptr(best), _ptr(best_idx), _ptr(scr), self._stream()))
+            self._planes_ok = not want_var  # (the variance pass turns the sigma_x plane into log EKLD)
+        return dict(score=score, var=var, logk=None, best=best, best_idx=best_idx, rec=rec)
 
     def us_variance(self, X_grid, idx_offset=0):
         """Uncertainty-sampling comparator (``_sampler.py:506-514``): mean_s latent predictive variance + argmax."""
@@ -349,8 +371,15 @@ class StepGraph(object):
             r = engine.score(xd, idx_offset=idx_offset, form=form, want_var=want_var, want_logk=want_logk)
             if engine._comm is not None:
                 _ext.check(engine.lib.bode_ekld_argmax_nccl(engine._comm, _ptr(r["rec"]), _ptr(engine._gathered), engine._stream()))
+                self._host_rec.copy_(engine._gathered.view(-1), non_blocking=True)
+            else:
+                self._host_rec.copy_(r["rec"], non_blocking=True)
             return r
 
+        # the winner record(s) land in pinned host memory as the graph's last node: reading them costs one stream
+        # synchronisation, no separate device->host call
+        nrec = 2 * (engine._gathered.numel() // 2 if engine._comm is not None else 1)
+        self._host_rec = torch.empty(nrec, dtype=torch.int64).pin_memory()
         with torch.cuda.device(dev):
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -373,10 +402,11 @@ class StepGraph(object):
 
     def winner(self):
         """(best score, global index) after ``launch``: one device->host copy, np.argmax semantics across ranks."""
+        torch.cuda.current_stream(self.eng.device).synchronize()
+        rec = self._host_rec.numpy()
         if self.eng._comm is not None:
-            return _ext.argmax_combine(self.eng._gathered.cpu().numpy())
-        rec = self.out["rec"].cpu()
-        return float(rec[:1].view(torch.float64).item()), int(rec[1].item())
+            return _ext.argmax_combine(rec.reshape(-1, 2))
+        return float(rec[:1].view(np.float64)[0]), int(rec[1])
 
     def run(self):
         self.launch()

@@ -109,6 +109,15 @@ int bode_ekld_score_dev(const void* workspace, int n, int d, int S, const double
                         int64_t idx_offset, int form, double* logk, double* score, double* var, double* best,
                         int64_t* best_idx, void* scratch, void* stream);
 
+/* The other EKLD form from the planes of the previous call: re-runs only k_ekld_reduce (xik, v, EKLD, log, mean / var,
+ * argmax) on the sigma_x and w.k planes that the last bode_ekld_score_dev call with the same workspace, X_design, Nd,
+ * scratch and with logk == NULL and var == NULL left in `scratch` (a call with logk or var turns the sigma_x plane into
+ * log EKLD and cannot be followed by this).  What `KLSampler`'s check of the `log1p` form against the literal expression
+ * of `_sampler.py:480` costs: 3 % of a scoring call instead of a second one.  `var` is nullable. */
+int bode_ekld_rescore_dev(const void* workspace, int n, int d, int S, const double* X_design, int64_t Nd,
+                          int64_t idx_offset, int form, double* score, double* var, double* best, int64_t* best_idx,
+                          void* scratch, void* stream);
+
 /* Same as bode_ekld_score_dev, and additionally times the dominant kernel (the fused K2-K4 scoring kernel) with
  * CUDA events recorded on `stream`; synchronises on the stop event before returning.  Used by bench.py for the
  * roofline figure. */

@@ -14,12 +14,14 @@ class OracleEngine(object):
         self.fail_samples = tuple(fail_samples)  # hyper-sample rows reported as not positive definite
         self.jitter_used = None
         self._comm = None
-        self.calls = dict(prepare=0, score=0, loglik=0, us=0)
+        self.calls = dict(prepare=0, score=0, rescore=0, loglik=0, us=0)
+        self._planes = None
 
     def prepare(self, X, Y, hyp, nugget_var, jitter=1e-8, quad=None, jitchol_retries=0):
         self.X, self.Y, self.hyp = np.array(X, dtype=float), np.array(Y, dtype=float), np.array(hyp, dtype=float)
         self.nugget, self.quad = float(np.sqrt(nugget_var)), quad
         self.calls["prepare"] += 1
+        self._planes = None
         info = np.zeros(self.hyp.shape[0], dtype=np.int32)
         for s in self.fail_samples:
             info[s] = 1
@@ -32,9 +34,18 @@ class OracleEngine(object):
     def mu_sigma(self):
         return orc.get_mu_sigma(self.X, self.Y, self.hyp, self.nugget)
 
+    def rescore(self, idx_offset=0, form=0, want_var=True):
+        # like EkldEngine.rescore: only after score(want_var=False, want_logk=False) on the same prepared state
+        if self._planes is None:
+            raise RuntimeError("rescore() must follow score(want_var=False, want_logk=False) on the same prepared state")
+        self.calls["rescore"] += 1
+        self.calls["score"] -= 1
+        return self.score(self._planes, idx_offset=idx_offset, form=form, want_var=want_var, want_logk=not want_var)
+
     def score(self, X_design, idx_offset=0, form=0, want_var=True, **kw):
         self.calls["score"] += 1
         Xd = np.atleast_2d(np.asarray(X_design, dtype=float))
+        self._planes = Xd if (not want_var and not kw.get("want_logk", True)) else None
         r = orc.score(self.X, self.Y, Xd, self.hyp, nugget=self.nugget, quad=self.quad)
         sc = torch.from_numpy(r["score"].copy())
         j = int(np.argmax(r["score"]))

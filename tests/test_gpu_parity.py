@@ -367,6 +367,28 @@ def test_logk_is_optional_in_the_c_abi(engine, ext):
     assert torch.equal(score, full["score"]) and int(rec[1]) == int(full["best_idx"]) and torch.equal(rec, full["rec"])
 
 
+def test_rescore_reuses_the_planes_of_the_previous_call(engine):
+    """`bode_ekld_rescore_dev`: the other EKLD form from the sigma_x / w.k planes of the previous call (reduction kernel
+    only) is bitwise what a full scoring call of that form returns; KLSampler's form check rides on it."""
+    import torch
+    X, Y, Xd, hyp = cases.make_problem(5, 60, 7, 3000, seed=21, ell_lo=0.2, ell_hi=0.8)
+    engine.prepare(X, Y, hyp, 1e-6)
+    full = {f: engine.score(Xd, idx_offset=11, form=f, want_var=True, want_logk=False) for f in (0, 1)}
+    full = {f: {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in r.items()} for f, r in full.items()}
+    first = engine.score(Xd, idx_offset=11, form=0, want_var=False, want_logk=False)
+    assert torch.equal(first["score"], full[0]["score"]) and torch.equal(first["rec"], full[0]["rec"])
+    again = engine.rescore(idx_offset=11, form=0, want_var=False)        # planes still intact: can be repeated
+    assert torch.equal(again["score"], full[0]["score"])
+    other = engine.rescore(idx_offset=11, form=1, want_var=True)
+    for k in ("score", "var", "rec"):
+        assert torch.equal(other[k], full[1][k]), k
+    with pytest.raises(RuntimeError, match="rescore"):                   # the variance pass consumed the planes
+        engine.rescore(form=0)
+    engine.prepare(X, Y, hyp, 1e-6)
+    with pytest.raises(RuntimeError, match="rescore"):                   # and so does a new prepare
+        engine.rescore(form=0)
+
+
 def _nccl_worker(rank, world, port, payload, q):
     import torch
     import torch.distributed as tdist

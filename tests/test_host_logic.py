@@ -270,7 +270,8 @@ def test_log1p_form_default_is_loud_when_it_changes_the_choice(capsys):
             if form == 0:
                 j = (int(torch.argmax(r["score"])) + 1) % r["score"].numel()   # a NaN next to the true winner
                 sc = r["score"].clone(); sc[j] = float("nan")
-                r.update(score=sc, best=sc[j:j + 1].clone(), best_idx=torch.tensor([idx_offset + j]))
+                r.update(score=sc, best=sc[j:j + 1].clone(), best_idx=torch.tensor([idx_offset + j]),
+                         rec=torch.cat([sc[j:j + 1].clone().view(torch.int64), torch.tensor([idx_offset + j])]))
             return r
 
     hyp = np.array([[1.0, 0.3], [2.0, 0.4]])
@@ -283,3 +284,8 @@ def test_log1p_form_default_is_loud_when_it_changes_the_choice(capsys):
     assert "WARNING" not in capsys.readouterr().out
     off = _tiny_sampler(TwoFaced(), hyp, ekld_form_check=False)
     assert "idx_best_literal" not in off.score_designs(np.linspace(0.05, 0.95, 12)[:, None])
+    # the check is one scoring call plus a re-run of the reduction on its planes, not two scoring calls
+    assert quiet.engine.calls["score"] == 1 and quiet.engine.calls["rescore"] == 1
+    assert off.engine.calls["score"] == 1 and off.engine.calls["rescore"] == 0
+    with pytest.raises(RuntimeError, match="rescore"):
+        off.engine.rescore()

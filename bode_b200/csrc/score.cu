@@ -1088,11 +1088,11 @@ int plan_score(const Layout& L, int64_t Nd, int sm_count, size_t smem_optin, Sco
     int rem = L.S, pos = 0, nt = 0;
     while (rem > 0 && nt < kMaxTail) {
       const int c = (nt == kMaxTail - 1) ? rem : (rem + 1) / 2;
-      P->tail_s0[nt++] = (unsigned short)pos;
+      P->tail_s0[nt++] = pos;
       pos += c;
       rem -= c;
     }
-    P->tail_s0[nt] = (unsigned short)pos;
+    P->tail_s0[nt] = pos;
     P->n_tail = nt;
     P->n_main = 0;
     sc = (L.S + 1) / 2;  // (reported: the largest item)

@@ -26,7 +26,7 @@ struct ScoreArgs {
   int S;
   int sc;            // hyper-samples per work item of the n_main equal chunks [i sc, (i+1) sc) ...
   int n_main, n_tail;                    // ... followed by n_tail tapered chunks [tail_s0[j], tail_s0[j+1])
-  unsigned short tail_s0[kMaxTail + 1];
+  int tail_s0[kMaxTail + 1];
   int ntiles;        // candidate tiles
   int form, mode;
   int debug_skip;    // developer timing knob (env BODE_DEBUG_SKIP): 1 = skip phase A after the first sample, 2 = skip phase B's DMMAs
@@ -42,7 +42,7 @@ struct ScorePlan {
   int rg, cg, rt, ct, C;
   int sc, ntiles;
   int n_main, n_tail;
-  unsigned short tail_s0[kMaxTail + 1];
+  int tail_s0[kMaxTail + 1];
   int64_t nitems;
   int stages, chunk_max, nchunks, u_global;
   size_t smem;

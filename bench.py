@@ -377,7 +377,7 @@ def main():
         saved_fd = os.dup(1)
         os.dup2(2, 1)
         try:
-            eng.init_nccl(tdist.group.WORLD)  # our own communicator for the C-ABI argmax exchange
+            eng.init_exchange(tdist.group.WORLD)  # the C-ABI argmax exchange: peer-memory mailboxes on one node, else NCCL
             eng.exchange_best(None)
             torch.cuda.synchronize()
         finally:
@@ -578,7 +578,8 @@ def bench_dense(args, cfg, eng, world, rank, local_rank, barrier, cpu_pool):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": cfg["name"],
                    "step": "prepare (S Cholesky, tensor pipe) + k_score over the rank's candidates (sigma_x, w.k) + xik/EKLD/log + in-order "
-                           "reduction over hyper-samples + argmax" + (" + one 16-byte ncclAllGather (C ABI)" if world > 1 else ""),
+                           "reduction over hyper-samples + argmax" + ((" + 16-byte argmax exchange over NVLink peer memory (bode_ekld_argmax_p2p, one warp)" if eng._xchg is not None
+                                                                    else " + one 16-byte ncclAllGather (C ABI)") if world > 1 else ""),
                    "l2": "flushed between timed iterations (256 MB write)",
                    "launch": "the step's copies and kernels are captured once into a CUDA graph (bode_b200.engine.StepGraph) and replayed" if use_graph else "plain launches",
                    "sharding": "fixed design of %d candidates split into contiguous blocks of %d per rank" % (Nd, hi - lo),

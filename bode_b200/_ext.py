@@ -25,6 +25,7 @@ EXPORTS = (
     "bode_ekld_prepare_quad_dev", "bode_ekld_score_quad_dev", "bode_ekld_score_host", "bode_gp_loglik_host", "bode_gp_loglik_dev", "bode_ekld_plan_describe", "bode_fp64_peak",
     "bode_tuning_reload", "bode_ctx_create", "bode_ctx_destroy", "bode_ctx_alloc_count", "bode_ekld_score_host_ctx", "bode_gp_loglik_host_ctx",
     "bode_nccl_unique_id", "bode_nccl_comm_create", "bode_nccl_comm_destroy", "bode_ekld_argmax_nccl", "bode_argmax_combine",
+    "bode_xchg_create", "bode_xchg_connect", "bode_xchg_destroy", "bode_ekld_argmax_p2p",
     "bode_ekld_prepare_jitter_dev", "bode_ekld_prepare_quad_rm_dev",
 )
 
@@ -136,6 +137,14 @@ def load():
     lib.bode_ekld_argmax_nccl.argtypes = [c_dp, c_dp, c_dp, c_dp]
     lib.bode_argmax_combine.restype = ctypes.c_int
     lib.bode_argmax_combine.argtypes = [c_dp, ctypes.c_int, c_dp, c_dp]
+    lib.bode_xchg_create.restype = ctypes.c_int
+    lib.bode_xchg_create.argtypes = [ctypes.c_int, ctypes.c_int, c_dp, c_dp]
+    lib.bode_xchg_connect.restype = ctypes.c_int
+    lib.bode_xchg_connect.argtypes = [c_dp, c_dp]
+    lib.bode_xchg_destroy.restype = ctypes.c_int
+    lib.bode_xchg_destroy.argtypes = [c_dp]
+    lib.bode_ekld_argmax_p2p.restype = ctypes.c_int
+    lib.bode_ekld_argmax_p2p.argtypes = [c_dp, c_dp, c_dp, c_dp]
     _lib = lib
     return lib
 

@@ -157,8 +157,8 @@ class KLSampler(object):
             if tdist.is_available() and tdist.is_initialized() and tdist.get_world_size(process_group) > 1:
                 self._sharded = True
                 self._lead = tdist.get_rank(process_group) == 0
-                if hasattr(engine, "init_nccl") and getattr(engine, "_comm", None) is None and tdist.get_backend(process_group) == "nccl":
-                    engine.init_nccl(process_group)
+                if hasattr(engine, "init_exchange") and not engine.has_exchange() and tdist.get_backend(process_group) == "nccl":
+                    engine.init_exchange(process_group)
         self.model = self.make_model(self.X, self.Y, it=0, mcmc=self.mcmc_model)
         self.model_d = self.make_model(self.X_u, self.Y_u, it=0, mcmc=self.mcmc_model)
         self.all_p = {}

@@ -205,6 +205,71 @@ static bool rec_better(double av, int64_t ai, double bv, int64_t bi) {
   return ai < bi;
 }
 
+
+// ---- peer-memory argmax exchange (no NCCL on the data path) -------------------------------------------------------
+// Every rank owns a mailbox of 2 (epoch parity) x world slots of 32 bytes {best, best_idx, epoch, pad}, mapped into
+// every other rank's address space (CUDA IPC).  One launch of one warp per step: lane r stores this rank's record into
+// slot [parity][my rank] of rank r's mailbox (NVLink peer stores, system-scope release of the epoch word), then waits
+// for slot [parity][r] of its own mailbox to carry the current epoch and copies it to `gathered`.  The epoch lives in
+// device memory (the launch is replayed from CUDA graphs with frozen arguments); slots alternate with its parity, so
+// a rank two steps ahead cannot exist (it would need this rank's flag of the step in between).
+constexpr int kMaxXchgRanks = 32;  // one lane per rank
+
+struct XchgDev {
+  unsigned long long* peer[kMaxXchgRanks];  // mailbox of every rank in this process's address space
+  unsigned long long* epoch;               // this rank's step counter
+  int world, rank;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__global__ void __launch_bounds__(32) k_argmax_exchange(XchgDev x, const unsigned long long* __restrict__ rec,
+                                                        unsigned long long* __restrict__ gathered, unsigned long long timeout_ns) {
+  const int lane = threadIdx.x;
+  const unsigned long long e = *x.epoch + 1ull;
+  const int par = (int)(e & 1ull);
+  __syncwarp();
+  if (lane < x.world) {
+    unsigned long long* dst = x.peer[lane] + (size_t)(par * x.world + x.rank) * 4;
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(rec[0]) : "memory");
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst + 1), "l"(rec[1]) : "memory");
+    st_release_sys(dst + 2, e);
+    const unsigned long long* src = x.peer[x.rank] + (size_t)(par * x.world + lane) * 4;
+    const unsigned long long t0 = globaltimer_ns();
+    bool ok = true;
+    while (ld_acquire_sys(src + 2) != e) {
+      if (globaltimer_ns() - t0 > timeout_ns) { ok = false; break; }
+      __nanosleep(64);
+    }
+    unsigned long long v0, v1;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v0) : "l"(src) : "memory");
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v1) : "l"(src + 1) : "memory");
+    // a peer that never arrived: NaN with index -2 (bode_argmax_combine reports it instead of picking a winner)
+    gathered[2 * lane] = ok ? v0 : 0x7ff8000000000000ull;
+    gathered[2 * lane + 1] = ok ? v1 : (unsigned long long)(-2ll);
+  }
+  __syncwarp();
+  if (lane == 0) *x.epoch = e;
+}
+
+struct bode_xchg {
+  XchgDev dev;
+  unsigned long long* mailbox = nullptr;  // own allocation
+  int device = -1;
+};
+
 extern "C" {
 
 const char* bode_version(void) { return "bode_b200 0.2.0 (sm_100a)"; }
@@ -665,6 +730,63 @@ int bode_ekld_argmax_nccl(void* comm, const void* best_rec, void* gathered, void
   return r == 0 ? BODE_OK : nccl_fail(r, "ncclAllGather");
 }
 
+int bode_xchg_create(int world, int rank, bode_xchg** out, unsigned char handle[64]) {
+  if (!out || !handle || world < 1 || world > kMaxXchgRanks || rank < 0 || rank >= world) return BODE_ERR_BAD_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  bode_xchg* x = new bode_xchg();
+  memset(&x->dev, 0, sizeof(x->dev));
+  x->dev.world = world;
+  x->dev.rank = rank;
+  const size_t bytes = (size_t)2 * world * 32 + 64;  // the slots, then the epoch counter
+  cudaError_t e = cudaGetDevice(&x->device);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&x->mailbox), bytes);
+  if (e == cudaSuccess) e = cudaMemset(x->mailbox, 0, bytes);
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, x->mailbox);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    if (x->mailbox) cudaFree(x->mailbox);
+    delete x;
+    return cuda_fail(e, "bode_xchg_create");
+  }
+  memcpy(handle, &h, 64);
+  x->dev.peer[rank] = x->mailbox;
+  x->dev.epoch = x->mailbox + (size_t)2 * world * 4;
+  *out = x;
+  return BODE_OK;
+}
+
+int bode_xchg_connect(bode_xchg* x, const unsigned char* handles /* world x 64 bytes, rank order */) {
+  if (!x || !handles) return BODE_ERR_BAD_ARG;
+  for (int r = 0; r < x->dev.world; r++) {
+    if (r == x->dev.rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)64 * r, 64);
+    void* p = nullptr;
+    BODE_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    x->dev.peer[r] = static_cast<unsigned long long*>(p);
+  }
+  return BODE_OK;
+}
+
+int bode_xchg_destroy(bode_xchg* x) {
+  if (!x) return BODE_ERR_BAD_ARG;
+  for (int r = 0; r < x->dev.world; r++)
+    if (r != x->dev.rank && x->dev.peer[r]) cudaIpcCloseMemHandle(x->dev.peer[r]);
+  if (x->mailbox) cudaFree(x->mailbox);
+  delete x;
+  return BODE_OK;
+}
+
+int bode_ekld_argmax_p2p(bode_xchg* x, const void* best_rec, void* gathered, void* stream) {
+  if (!x || !best_rec || !gathered) return BODE_ERR_BAD_ARG;
+  k_argmax_exchange<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(x->dev, static_cast<const unsigned long long*>(best_rec),
+                                                                     static_cast<unsigned long long*>(gathered),
+                                                                     5000000000ull /* 5 s: a peer that does not show up */);
+  BODE_CUDA(cudaGetLastError());
+  return BODE_OK;
+}
+
 int bode_argmax_combine(const void* records, int count, double* best, int64_t* best_idx) {
   if (!records || count < 1 || !best || !best_idx) return BODE_ERR_BAD_ARG;
   const char* p = static_cast<const char*>(records);
@@ -675,6 +797,7 @@ int bode_argmax_combine(const void* records, int count, double* best, int64_t* b
     int64_t idx;
     memcpy(&v, p + 16 * i, 8);
     memcpy(&idx, p + 16 * i + 8, 8);
+    if (idx == -2) return BODE_ERR_NCCL;  // bode_ekld_argmax_p2p: a peer did not deliver its record in time
     if (idx < 0) continue;  // a rank without candidates
     if (bi < 0 || rec_better(v, idx, bv, bi)) { bv = v; bi = idx; }
   }

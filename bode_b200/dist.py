@@ -108,7 +108,7 @@ def sharded_score(engine, X_design, form=0, group=None, want_scores=True, want_v
     ws, rank = dist.get_world_size(group), dist.get_rank(group)
     lo, hi = shard_bounds(Nd, ws, rank)
     dev = engine.device
-    use_capi = getattr(engine, "_comm", None) is not None  # EkldEngine.init_nccl(): C-ABI exchange on the compute stream
+    use_capi = bool(getattr(engine, "has_exchange", lambda: getattr(engine, "_comm", None) is not None)())  # C-ABI exchange on the compute stream
     if hi > lo:
         r = run(Xd[lo:hi], lo)
         bv, bi, sc, vr, rec = r["best"], r["best_idx"], r["score"], r["var"], r.get("rec")

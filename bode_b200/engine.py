@@ -39,6 +39,7 @@ class EkldEngine:
         self._ndim = 0
         self._prepared = False
         self._comm = None          # our own NCCL communicator (init_nccl), world size / rank
+        self._xchg = None          # peer-memory mailboxes (init_p2p): the argmax exchange as one kernel over NVLink
         self._world = 1
         self._rank = 0
         self._gathered = None
@@ -68,7 +69,75 @@ class EkldEngine:
             self._gathered = torch.empty(2 * world, dtype=torch.int64, device=self.device)
         return self
 
+    def init_p2p(self, group=None):
+        """Peer-memory form of the exchange (``bode_ekld_argmax_p2p``): every rank's mailbox is exported as a CUDA IPC
+        handle, torch.distributed carries the 64-byte handles, every rank maps its peers'.  One process per GPU, same
+        node, peer access between the GPUs.  Collective; raises BodeError on the rank where the mapping fails."""
+        import torch.distributed as tdist
+        world, rank = tdist.get_world_size(group), tdist.get_rank(group)
+        with torch.cuda.device(self.device):
+            handle = (ctypes.c_ubyte * 64)()
+            x = ctypes.c_void_p()
+            _ext.check(self.lib.bode_xchg_create(world, rank, ctypes.byref(x), handle))
+            mine = torch.tensor(list(handle), dtype=torch.uint8)
+            on_dev = tdist.get_backend(group) == "nccl"
+            mine = mine.to(self.device) if on_dev else mine
+            allh = torch.empty(64 * world, dtype=torch.uint8, device=mine.device)
+            tdist.all_gather_into_tensor(allh, mine, group=group)
+            raw = bytes(allh.cpu().tolist())
+            try:
+                _ext.check(self.lib.bode_xchg_connect(x, ctypes.c_char_p(raw)))
+            except _ext.BodeError:
+                self.lib.bode_xchg_destroy(x)
+                raise
+            self._xchg, self._world, self._rank, self._group = x, world, rank, group
+            self._gathered = torch.empty(2 * world, dtype=torch.int64, device=self.device)
+            torch.cuda.synchronize(self.device)
+        tdist.barrier(group)  # nobody stores into a mailbox that is not mapped everywhere yet
+        return self
+
+    def init_exchange(self, group=None):
+        """The multi-GPU argmax exchange: peer memory when every rank can map every mailbox (one node), else NCCL.
+        ``BODE_EXCHANGE=nccl|p2p`` forces one.  Collective."""
+        import os
+        import torch.distributed as tdist
+        want = os.environ.get("BODE_EXCHANGE", "auto")
+        if want == "nccl":
+            return self.init_nccl(group)
+        if want == "p2p":
+            return self.init_p2p(group)
+        ok = 1
+        try:
+            self.init_p2p(group)
+        except _ext.BodeError:
+            ok = 0
+            tdist.barrier(group)  # (the barrier the failed init_p2p did not reach)
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device if tdist.get_backend(group) == "nccl" else "cpu")
+        tdist.all_reduce(flag, op=tdist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            self.close_p2p()
+            return self.init_nccl(group)
+        return self
+
+    def has_exchange(self):
+        return self._comm is not None or self._xchg is not None
+
+    def _enqueue_exchange(self, rec):
+        if self._xchg is not None:
+            _ext.check(self.lib.bode_ekld_argmax_p2p(self._xchg, _ptr(rec), _ptr(self._gathered), self._stream()))
+        else:
+            _ext.check(self.lib.bode_ekld_argmax_nccl(self._comm, _ptr(rec), _ptr(self._gathered), self._stream()))
+
+    def close_p2p(self):
+        if self._xchg is not None:
+            torch.cuda.synchronize(self.device)
+            self.lib.bode_xchg_destroy(self._xchg)
+            self._xchg = None
+
     def close_nccl(self):
+        """Release the exchange.  StepGraph objects built on this engine must be deleted first: NCCL does not destroy a
+        communicator while a CUDA graph that captured one of its collectives is alive."""
+        self.close_p2p()
         if self._comm is not None:
             torch.cuda.synchronize(self.device)
             self.lib.bode_nccl_comm_destroy(self._comm)
@@ -78,12 +147,12 @@ class EkldEngine:
         """All ranks: one 16-byte ncclAllGather of the packed (best, idx) record on the compute stream, ONE device->host
         copy, np.argmax semantics on the host.  ``rec``: the int64[2] tensor of ``score()['rec']`` (or None for a rank
         without candidates)."""
-        if self._comm is None:
-            raise RuntimeError("call init_nccl() first")
+        if not self.has_exchange():
+            raise RuntimeError("call init_exchange() / init_nccl() / init_p2p() first")
         with torch.cuda.device(self.device):
             if rec is None:
                 rec = torch.tensor([0, -1], dtype=torch.int64, device=self.device)
-            _ext.check(self.lib.bode_ekld_argmax_nccl(self._comm, _ptr(rec), _ptr(self._gathered), self._stream()))
+            self._enqueue_exchange(rec)
             host = self._gathered.cpu().numpy()
         return _ext.argmax_combine(host)
 
@@ -149,7 +218,7 @@ class EkldEngine:
                     raise ValueError("one weight per quadrature point")
                 Nq = Xq.shape[0]
                 qs = self._buf("quad_scratch", self.lib.bode_quad_scratch_bytes(n, S, Nq), torch.uint8)
-                if self._comm is not None and self._world > 1 and Nq >= 64 * self._world:
+                if self.has_exchange() and self._world > 1 and Nq >= 64 * self._world:
                     # several GPUs (init_nccl): the O(Nq^2 S) row means of the quadrature points are computed in row shards
                     # and all-gathered (torch.distributed plumbing); sigma0_q is then formed from identical numbers in the
                     # same order on every rank -- bit-identical to the single-GPU preparation
@@ -369,8 +438,8 @@ class StepGraph(object):
                 xd = to(xd)
             self._xd = xd
             r = engine.score(xd, idx_offset=idx_offset, form=form, want_var=want_var, want_logk=want_logk)
-            if engine._comm is not None:
-                _ext.check(engine.lib.bode_ekld_argmax_nccl(engine._comm, _ptr(r["rec"]), _ptr(engine._gathered), engine._stream()))
+            if engine.has_exchange():
+                engine._enqueue_exchange(r["rec"])
                 self._host_rec.copy_(engine._gathered.view(-1), non_blocking=True)
             else:
                 self._host_rec.copy_(r["rec"], non_blocking=True)
@@ -378,7 +447,7 @@ class StepGraph(object):
 
         # the winner record(s) land in pinned host memory as the graph's last node: reading them costs one stream
         # synchronisation, no separate device->host call
-        nrec = 2 * (engine._gathered.numel() // 2 if engine._comm is not None else 1)
+        nrec = 2 * (engine._gathered.numel() // 2 if engine.has_exchange() else 1)
         self._host_rec = torch.empty(nrec, dtype=torch.int64).pin_memory()
         with torch.cuda.device(dev):
             side = torch.cuda.Stream()
@@ -404,7 +473,7 @@ class StepGraph(object):
         """(best score, global index) after ``launch``: one device->host copy, np.argmax semantics across ranks."""
         torch.cuda.current_stream(self.eng.device).synchronize()
         rec = self._host_rec.numpy()
-        if self.eng._comm is not None:
+        if self.eng.has_exchange():
             return _ext.argmax_combine(rec.reshape(-1, 2))
         return float(rec[:1].view(np.float64)[0]), int(rec[1])
 

@@ -38,7 +38,8 @@ typedef enum bode_status {
   BODE_ERR_WORKSPACE = -3,   /* workspace too small / misaligned */
   BODE_ERR_CUDA = -4,        /* CUDA runtime error (see bode_last_cuda_error) */
   BODE_ERR_NOT_PD = -5,      /* host entry points only: a Cholesky pivot was non-positive (info[s] > 0) */
-  BODE_ERR_NCCL = -6         /* libnccl.so.2 not loadable, or an NCCL call failed (see bode_last_cuda_error) */
+  BODE_ERR_NCCL = -6         /* libnccl.so.2 not loadable, an NCCL call failed (see bode_last_cuda_error), or a peer did not
+                                deliver its record to bode_ekld_argmax_p2p */
 } bode_status;
 
 #define BODE_MAX_N 1024 /* observations */
@@ -211,6 +212,23 @@ int bode_nccl_comm_create(const void* id128, int world, int rank, void** comm);
 int bode_nccl_comm_destroy(void* comm);
 int bode_ekld_argmax_nccl(void* comm, const void* best_rec, void* gathered, void* stream);
 int bode_argmax_combine(const void* records_host, int count, double* best, int64_t* best_idx);
+
+/* The same exchange WITHOUT NCCL on the data path: one kernel over NVLink peer memory.  Every rank owns a mailbox of
+ * 2 x world 32-byte slots {best, best_idx, epoch}, exported as a CUDA IPC handle and mapped by every other rank (one
+ * process per GPU, same node).  bode_ekld_argmax_p2p enqueues one warp on `stream`: lane r stores this rank's record
+ * into its slot of rank r's mailbox (system-scope release of the epoch word) and then waits for rank r's record in its
+ * own mailbox; gathered[16 * world] (device) is filled exactly like the NCCL form.  The epoch counter lives in device
+ * memory, so the launch replays from a CUDA graph; slots alternate with the epoch's parity.  A peer that does not
+ * deliver within 5 s leaves {NaN, -2} in its slot and bode_argmax_combine returns BODE_ERR_NCCL.  Collective: every rank
+ * must enqueue the same number of calls.
+ *   bode_xchg_create(world, rank, &x, handle)   allocates the mailbox, returns its 64-byte IPC handle
+ *   bode_xchg_connect(x, handles)               handles = the world handles in rank order (distributed by the caller);
+ *                                               synchronise the ranks (a barrier) between connect and the first exchange */
+typedef struct bode_xchg bode_xchg;
+int bode_xchg_create(int world, int rank, bode_xchg** x, unsigned char handle[64]);
+int bode_xchg_connect(bode_xchg* x, const unsigned char* handles);
+int bode_xchg_destroy(bode_xchg* x);
+int bode_ekld_argmax_p2p(bode_xchg* x, const void* best_rec, void* gathered, void* stream);
 
 /* Host-only: JSON description of the launch plan the scoring entry points would use for this shape on a device with
  * `sm_count` SMs and `smem_optin` bytes of opt-in shared memory per CTA (kernel variant, candidates per CTA, ring

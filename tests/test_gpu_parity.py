@@ -389,7 +389,7 @@ def test_rescore_reuses_the_planes_of_the_previous_call(engine):
         engine.rescore(form=0)
 
 
-def _nccl_worker(rank, world, port, payload, q):
+def _nccl_worker(rank, world, port, payload, q, kind="nccl"):
     import torch
     import torch.distributed as tdist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -400,7 +400,8 @@ def _nccl_worker(rank, world, port, payload, q):
         from bode_b200 import dist as bdist
         from bode_b200.engine import EkldEngine
         X, Y, Xd, hyp = payload
-        eng = EkldEngine().init_nccl(tdist.group.WORLD)
+        eng = getattr(EkldEngine(), "init_" + kind)(tdist.group.WORLD)
+        assert (eng._xchg is not None) == (kind == "p2p")
         eng.prepare(X, Y, hyp, 1e-6)
         res = bdist.sharded_score(eng, Xd, group=tdist.group.WORLD)
         empty = bdist.sharded_score(eng, Xd[:1], group=tdist.group.WORLD)   # rank 1 has no candidates
@@ -409,16 +410,29 @@ def _nccl_worker(rank, world, port, payload, q):
         eng.prepare(X, Y, hyp, 1e-6, quad=(Xq, None))
         mq = eng.mu_sigma()
         rq = bdist.sharded_score(eng, Xd[:500], group=tdist.group.WORLD)
+        # the captured step (copies + prepare + score + exchange as one CUDA graph), replayed: the exchange's epoch
+        # counter and slot parity advance on the device
+        from bode_b200.engine import StepGraph
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        lo, hi = bdist.shard_bounds(Xd.shape[0], world, rank)
+        sg = StepGraph(eng, pin(X), pin(Y), pin(hyp), torch.from_numpy(Xd[lo:hi]).cuda(), 1e-6, idx_offset=lo)
+        wins = [sg.run() for _ in range(5)]
+        del sg  # a CUDA graph that captured a collective must be gone before its communicator is destroyed
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
         q.put((rank, res["idx_best"], res["best"], res["score"].tolist(), res["var"].tolist(), empty["idx_best"],
-               list(mq), rq["score"].tolist(), rq["idx_best"]))
+               list(mq), rq["score"].tolist(), rq["idx_best"], wins))
         eng.close_nccl()
     finally:
         tdist.destroy_process_group()
 
 
-def test_two_ranks_over_nccl_match_single_rank_bitwise(engine):
+@pytest.mark.parametrize("kind", ["nccl", "p2p"])
+def test_two_ranks_over_nccl_match_single_rank_bitwise(engine, kind):
     """Two processes, one GPU each, candidate blocks sharded, the 16-byte argmax record exchanged by
-    `bode_ekld_argmax_nccl` (C ABI, our own communicator): scores, variance and winner identical to one rank, bit for bit."""
+    `bode_ekld_argmax_nccl` (C ABI, our own communicator) or by `bode_ekld_argmax_p2p` (one warp storing into the peers'
+    IPC-mapped mailboxes over NVLink): scores, variance and winner identical to one rank, bit for bit."""
     import socket
     import torch
     import torch.multiprocessing as mp
@@ -430,7 +444,7 @@ def test_two_ranks_over_nccl_match_single_rank_bitwise(engine):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, (X, Y, Xd, hyp), q)) for r in range(2)]
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, (X, Y, Xd, hyp), q, kind)) for r in range(2)]
     [p.start() for p in procs]
     out = sorted(q.get(timeout=300) for _ in range(2))
     [p.join(timeout=120) for p in procs]
@@ -441,8 +455,9 @@ def test_two_ranks_over_nccl_match_single_rank_bitwise(engine):
     engine.prepare(X, Y, hyp, 1e-6, quad=(Xq, None))
     mq1 = engine.mu_sigma()
     rq1 = engine.score(Xd[:500])
-    for rank, idx, best, score, var, idx_empty, mq, sq, iq in out:
+    for rank, idx, best, score, var, idx_empty, mq, sq, iq, wins in out:
         assert (idx, best) == one_best
+        assert all((int(i), float(b)) == one_best for b, i in wins), wins
         np.testing.assert_array_equal(np.array(score), one_score)
         np.testing.assert_array_equal(np.array(var), one_var)
         assert idx_empty == 0

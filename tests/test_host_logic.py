@@ -215,6 +215,11 @@ def test_packed_record_and_c_abi_combine(built_lib):
     assert _ext.argmax_combine(empty.numpy()) == (0.5, 40)                       # idx < 0: rank without candidates
     host = dist.combine_argmax(torch.tensor(vals, dtype=torch.float64), torch.tensor([40, 30, 20, 10]))
     assert host == (2.0, 20)
+    # bode_ekld_argmax_p2p marks a peer that never delivered with {NaN, -2}: the combine reports it, it does not pick
+    late = torch.cat([recs, dist.pack_record(torch.tensor([float("nan")]), torch.tensor([-2]))])
+    with pytest.raises(_ext.BodeError) as e:
+        _ext.argmax_combine(late.numpy())
+    assert e.value.status == -6
 
 
 def test_reference_driver_source_runs_against_this_package(tmp_path):

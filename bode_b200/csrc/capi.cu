@@ -780,6 +780,9 @@ int bode_xchg_destroy(bode_xchg* x) {
 
 int bode_ekld_argmax_p2p(bode_xchg* x, const void* best_rec, void* gathered, void* stream) {
   if (!x || !best_rec || !gathered) return BODE_ERR_BAD_ARG;
+  int dev = -1;
+  BODE_CUDA(cudaGetDevice(&dev));
+  if (dev != x->device) return BODE_ERR_BAD_ARG;  // the mailbox belongs to the device it was created on
   k_argmax_exchange<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(x->dev, static_cast<const unsigned long long*>(best_rec),
                                                                      static_cast<unsigned long long*>(gathered),
                                                                      5000000000ull /* 5 s: a peer that does not show up */);

@@ -52,6 +52,7 @@ static Tuning read_tuning() {
   t.stages = geti("BODE_STAGES", 0);
   t.debug_skip = geti("BODE_DEBUG_SKIP", 0);
   t.stagger = geti("BODE_STAGGER", 0);
+  t.refill = geti("BODE_REFILL", 0);
   t.xik_series = geti("BODE_XIK_SERIES", 1);
   t.prep_variant = geti("BODE_PREP_VARIANT", -1);
   t.rowmean_variant = geti("BODE_ROWMEAN_VARIANT", -1);
@@ -483,6 +484,7 @@ static int score_common(const void* workspace, int n, int d, int S, const double
   memcpy(a.tail_s0, P.tail_s0, sizeof(a.tail_s0));
   a.debug_skip = tuning().debug_skip;
   a.stagger = tuning().stagger;
+  a.refill_last = tuning().refill;
   a.stages = P.stages; a.chunk_max = P.chunk_max; a.nchunks = P.nchunks; a.u_global = P.u_global;
   memcpy(a.chunk_g0, P.chunk_g0, sizeof(a.chunk_g0));
   memcpy(a.tile_id, P.tile_id, sizeof(a.tile_id));

@@ -395,6 +395,7 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
   int* aux_cnt = reinterpret_cast<int*>(bars + 2 * kMaxStages + 2);    // warps that finished phase A so far (all samples)
   int* chunk_off = aux_cnt + 2;                                         // [nchunks+1] offset (doubles) of chunk q inside M_s
   int* chunk_p0 = chunk_off + nchunks + 1;                              // [nchunks+2] first group PAIR of chunk q
+  int* stage_cnt = chunk_p0 + nchunks + 2;                              // [stages] warps that left the stage so far (all uses)
 
   // ---- work item ----
   const int item = blockIdx.x;
@@ -420,6 +421,7 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
     mbar_init(aux_full, 1);
     mbar_init(stagger, RG * ((CG + 1) / 2));
     aux_cnt[0] = 0;
+    for (int i = 0; i < stages; i++) stage_cnt[i] = 0;
     if (blockIdx.x == 0) *a.done_counter = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -482,7 +484,7 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
   const double* ring_lane = ring + lane;
 
   const int aux_ut_off = aux_ut(L);
-  int st = 0, it = 0;
+  int st = 0, it = 0, round_ = 1;  // round_: how many times the stages have been used, this use included
   uint32_t ph = 0;
   // refills trail the consumer by `lag` chunks so that the duty warp rarely has to wait for slower warps
   const int lag = (CG == 1 && stages >= 4) ? 2 : 1;  // (the lagging groups hold the duty when CG > 1: no extra lag needed)
@@ -557,7 +559,7 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
       constexpr int kDutyWarps = (CG > 1) ? RG * (CG / 2) : kWarps;
       const int dj = (it - lag) & (kDutyWarps - 1);
       const int duty_warp = (CG > 1) ? ((2 * (dj / RG) + 1) * RG + dj % RG) : dj;
-      if (it >= lag && duty_warp == warp) {
+      if (!a.refill_last && it >= lag && duty_warp == warp) {
         if (rf_ls < nsamp && !(a.debug_skip & 4) && elect_one()) {
           const int pst = (st >= lag) ? st - lag : st - lag + stages;
           TS_WAIT_BEGIN();
@@ -567,7 +569,7 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
         }
         __syncwarp();
       }
-      if (it >= lag) { if (++rf_q == nchunks) { rf_q = 0; rf_ls++; } }
+      if (!a.refill_last && it >= lag) { if (++rf_q == nchunks) { rf_q = 0; rf_ls++; } }
       next_cp = next_cp_pref;               // prefetched one transition ago (its shared-memory latency is off the path)
       next_cp_pref = chunk_p0[q + 2];
       TS_WAIT_BEGIN();
@@ -577,8 +579,22 @@ __global__ void __launch_bounds__(32 * RG * CG, (RG * CG <= 8 && RT * CT <= 16) 
     };
     auto leave = [&]() {  // done with chunk q
       __syncwarp();
-      if (lane == 0) mbar_arrive(empty0 + 8 * st);
-      if (++st == stages) { st = 0; ph ^= 1; }
+      if (a.refill_last) {
+        // The last warp to leave the stage refills it (chunk it + stages): a counter instead of the empty barrier, nobody
+        // waits.  acq_rel orders every warp's reads of the stage before the last arriver, which then crosses to the async
+        // proxy before the bulk copy overwrites it (same scheme as the aux block).
+        if (lane == 0) {
+          const int done = atom_add_acq_rel_smem(stage_cnt + st, 1) + 1;
+          if (done == kWarps * round_ && rf_ls < nsamp && !(a.debug_skip & 4)) {
+            fence_proxy_async_smem();
+            issue_chunk(rf_ls, rf_q, st);
+          }
+        }
+        if (++rf_q == nchunks) { rf_q = 0; rf_ls++; }
+      } else if (lane == 0) {
+        mbar_arrive(empty0 + 8 * st);
+      }
+      if (++st == stages) { st = 0; ph ^= 1; ++round_; }
       ++it;
     };
     enter();
@@ -937,7 +953,7 @@ static size_t score_smem_bytes(const Layout& L, int C, int RG, int nthreads, int
   size_t dbl = (size_t)L.npad * C + (u_global ? (size_t)aux_nw() : L.aux_doubles) + (size_t)stages * chunk_max + (size_t)RG * C + (size_t)nthreads / 2 +
                (size_t)C * 4 * L.dk;
   return dbl * sizeof(double) + sizeof(uint64_t) * (2 * kMaxStages + 3) +
-         sizeof(int) * (2 * (nchunks + 2) + 8) + 128;
+         sizeof(int) * (2 * (nchunks + 2) + 8 + kMaxStages) + 128;
 }
 
 // Longest-processing-time assignment of row tiles (weight R+1 ~ number of live k4 groups) to the row groups.

@@ -32,6 +32,7 @@ struct ScoreArgs {
   int debug_skip;    // developer timing knob (env BODE_DEBUG_SKIP): 1 = skip phase A after the first sample, 2 = skip phase B's DMMAs
   int stages, chunk_max /* doubles */, nchunks;
   int stagger;       // developer knob (env BODE_STAGGER): odd column groups start one phase A late
+  int refill_last;   // 1: the last warp to leave a ring stage issues its refill (shared-memory counter, nobody waits); 0: duty warp
   int u_global;      // 1: the tiled observations Ut and the (nun, w) pairs stay in global memory (large n)
   unsigned short chunk_g0[kMaxChunks + 1];
   short tile_id[kMaxRG * kMaxRT];  // [rg][slot], right-aligned ascending, -1 = unused

@@ -11,6 +11,7 @@ struct Tuning {
   int stages;         // BODE_STAGES         (ring stages, >= 2)
   int debug_skip;     // BODE_DEBUG_SKIP     (timing decomposition only)
   int stagger;        // BODE_STAGGER
+  int refill;         // BODE_REFILL         (1: the last warp to leave a ring stage refills it; 0: rotating duty warp)
   int xik_series;     // BODE_XIK_SERIES     (0: evaluate every xik factor with erf)
   int rowmean_variant;  // BODE_ROWMEAN_VARIANT (0: thread-per-point row means instead of the tensor-pipe variant)
   int prep_variant;   // BODE_PREP_VARIANT   (0: global-memory prepare kernel even where the shared-memory tile kernel fits)

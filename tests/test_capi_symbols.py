@@ -130,3 +130,19 @@ def test_launch_plan_small_problem_uses_all_sms(built_lib):
     buf = ctypes.create_string_buffer(4096)
     assert lib.bode_ekld_plan_describe(2000, 8, 4, 10, 148, 232448, buf, 4096) == -2
     assert lib.bode_ekld_plan_describe(10, 8, 4, 10, 148, 232448, buf, 8) == -1
+
+
+def test_sample_schedule_invariants_random_shapes(built_lib):
+    """The work-item schedule over random (n, S, Nd): chunks cover 0..S exactly once in descending size, items = tiles x
+    chunks, and a design with fewer tiles than SMs is still split into enough items to occupy most SMs (one full wave of
+    two-sample items can beat two waves of one-sample items, so not necessarily all of them)."""
+    from bode_b200 import _ext
+    rng = np.random.default_rng(77)
+    for _ in range(300):
+        n = int(rng.choice([1, 7, 30, 64, 200, 256, 500, 1000]))
+        S = int(rng.choice([1, 2, 3, 5, 16, 31, 60, 64, 100, 128, 257, 1000, 70000]))
+        Nd = int(rng.choice([1, 63, 64, 65, 1000, 9471, 9472, 12500, 100000, 1000000]))
+        p = _ext.plan_describe(n, 8, S, Nd)
+        _check_sample_schedule(p, S)
+        assert len(p["tail_s0"]) <= 25
+        assert 2 * p["items"] >= min(148, p["tiles"] * S) or p["tiles"] >= 148, (n, S, Nd, p["items"])
